@@ -1,0 +1,166 @@
+/*
+ * zpaqgpu.h -- C ABI of libzpaqgpu, the B200 (sm_100a) ZPAQ block codec.
+ *
+ * The reference (dy-tea/zpaq-v) has no FFI of its own; its boundary for this path is the V method
+ * surface zpaq.Compressor / zpaq.Decompresser.  Each entry point below names the reference
+ * interface it stands in for (file:line under /root/reference).  A V host binds these with
+ * `#flag -lzpaqgpu`, `#include "zpaqgpu.h"` and `fn C.zpaqgpu_*` declarations.
+ *
+ * Rules of the boundary: plain pointers and sizes only; the caller owns every host buffer; the
+ * library owns device memory and pinned staging; errors are negative status codes, never aborts;
+ * there is NO CPU fallback -- without a usable CUDA device every compute call returns
+ * ZPAQGPU_E_NODEVICE.  A ctx is bound to one device and is single-threaded; one process per GPU
+ * (or one ctx per GPU) is the multi-GPU model, no collective is involved because ZPAQ blocks are
+ * independent (compressor.v:84-187 re-initialises all model state in start_block).
+ */
+#ifndef ZPAQGPU_H
+#define ZPAQGPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+#if defined(__GNUC__)
+#pragma GCC visibility push(default) /* the library itself is built with -fvisibility=hidden */
+#endif
+
+typedef struct zpaqgpu_ctx zpaqgpu_ctx;
+
+enum {
+    ZPAQGPU_OK = 0,
+    ZPAQGPU_E_NODEVICE = -1, /* no CUDA device / driver; nothing is computed on the host instead */
+    ZPAQGPU_E_CUDA = -2,     /* a CUDA call failed; zpaqgpu_last_error() has the text           */
+    ZPAQGPU_E_NOSPACE = -3,  /* caller buffer too small; *need holds the required size          */
+    ZPAQGPU_E_ARG = -4,      /* bad argument                                                    */
+    ZPAQGPU_E_FORMAT = -5,   /* archive bytes the reference decoder would also reject           */
+    ZPAQGPU_E_UNSUPPORTED = -6, /* PCOMP/PROG post-processing, sizebits beyond device limits     */
+    ZPAQGPU_E_STATE = -7,    /* streaming call in the wrong state (the reference silently returns) */
+    ZPAQGPU_E_NOMEM = -8
+};
+
+/* Which kernel family a call may use.  AUTO picks the specialised ICM/ISSE-chain kernel when the
+ * header has that shape (all of -m1..-m5 do) and the generic all-components kernel otherwise. */
+enum { ZPAQGPU_KERNEL_AUTO = 0, ZPAQGPU_KERNEL_GENERIC = 1, ZPAQGPU_KERNEL_CHAIN = 2 };
+
+/* ---- lifetime -------------------------------------------------------------------------- */
+/* device < 0 selects the current CUDA device.  Replaces Compressor.new()/Decompresser.new()
+ * (compressor.v:33, decompressor.v:187) as the owner of all codec state. */
+int zpaqgpu_init(zpaqgpu_ctx **out, int device);
+void zpaqgpu_destroy(zpaqgpu_ctx *ctx);
+const char *zpaqgpu_strerror(int code);
+const char *zpaqgpu_last_error(const zpaqgpu_ctx *ctx);
+/* Optional tuning: kernel family (above), workspace budget in bytes (0 = 80% of free HBM),
+ * CUDA stream to run on (0 = the ctx's own stream). */
+int zpaqgpu_set_kernel(zpaqgpu_ctx *ctx, int kernel);
+int zpaqgpu_set_workspace_limit(zpaqgpu_ctx *ctx, uint64_t bytes);
+int zpaqgpu_set_stream(zpaqgpu_ctx *ctx, void *cuda_stream);
+
+/* ---- constant data --------------------------------------------------------------------- */
+/* get_compression_level(level).hcomp (levels.v:26-375): writes the header bytes
+ * "hh hm ph pm n comp.. 0 hcomp.. 0 [0]" and returns their count, or ZPAQGPU_E_NOSPACE. */
+int zpaqgpu_level_header(int level, uint8_t *out, int cap);
+/* The float-built lookup tables exactly as the device uses them (predictor.v:21-96):
+ * squash 4096 x int32, stretch 32768 x int32, state table 1024 x uint8 (statetable.v:15-57). */
+int zpaqgpu_tables(int32_t *squash4096, int32_t *stretch32768, uint8_t *state1024);
+
+/* ---- batch compression: the fast path -------------------------------------------------- */
+/* One ZPAQ block with one segment per input range, exactly the bytes that
+ *   Compressor.start_block(level); start_segment(name, comment); for compress(65536) {};
+ *   end_segment(); end_block()                       (compressor.v:79-413, cmd/main.v:298-311)
+ * writes for that range.  in_off/out_off have n_blocks+1 entries.  names/comments may be NULL
+ * (empty strings) or hold NUL-terminated strings per block (entries may be NULL).
+ * Returns ZPAQGPU_E_NOSPACE with *out_need set when out_cap is too small. */
+int zpaqgpu_compress_blocks(zpaqgpu_ctx *ctx, int level, const uint8_t *in, const uint64_t *in_off,
+                            int n_blocks, const char *const *names, const char *const *comments,
+                            uint8_t *out, uint64_t out_cap, uint64_t *out_off, uint64_t *out_need);
+/* Same with caller-supplied model header bytes in the levels.v layout (any header the reference
+ * decoder accepts, decompressor.v:278-342: all nine component types and arbitrary HCOMP). */
+int zpaqgpu_compress_blocks_header(zpaqgpu_ctx *ctx, const uint8_t *header, int header_len,
+                                   const uint8_t *in, const uint64_t *in_off, int n_blocks,
+                                   const char *const *names, const char *const *comments,
+                                   uint8_t *out, uint64_t out_cap, uint64_t *out_off,
+                                   uint64_t *out_need);
+/* Device-resident variant: d_in, d_in_off, d_out, d_out_off are device pointers on ctx's device;
+ * names/comments are empty.  d_out must hold out_cap bytes; *out_total receives the archive size.
+ * Synchronises the stream before returning. */
+int zpaqgpu_compress_blocks_dev(zpaqgpu_ctx *ctx, int level, const void *d_in, const void *d_in_off,
+                                const uint64_t *h_in_off, int n_blocks, void *d_out,
+                                uint64_t out_cap, void *d_out_off, uint64_t *out_total);
+
+/* ---- batch decompression --------------------------------------------------------------- */
+/* Decompresser.find_block's locator scan (decompressor.v:227-254) over a whole archive: offsets
+ * of the byte AFTER each 16-byte locator+"zPQ" match, ascending.  Returns ZPAQGPU_E_NOSPACE with
+ * *n_found = required count when cap is too small. */
+int zpaqgpu_find_blocks(zpaqgpu_ctx *ctx, const uint8_t *arc, uint64_t len, uint64_t *starts,
+                        int cap, int *n_found);
+
+typedef struct {
+    uint64_t block_start;  /* archive offset just after the locator (the level byte)            */
+    uint64_t block_end;    /* archive offset just after the block's 0xFF                        */
+    uint64_t name_off;     /* archive offset of the NUL-terminated filename                     */
+    uint64_t comment_off;  /* archive offset of the NUL-terminated comment                      */
+    uint64_t out_off;      /* where the segment's plaintext starts in `out`                     */
+    uint64_t out_len;      /* plaintext bytes                                                   */
+    int32_t block_index;   /* index of the block among the valid blocks of the archive          */
+    int32_t sha1_ok;       /* 1 stored SHA1 matches, 0 mismatch, -1 no checksum (marker 254)    */
+} zpaqgpu_segment;
+
+/* for find_block { for find_filename { decompress(-1); read_segment_end } } over the archive
+ * (decompressor.v:219-635, cmd/main.v:349-401): every segment's plaintext concatenated in
+ * archive order into `out`, one zpaqgpu_segment record each.  size_hints (may be NULL) gives an
+ * upper bound of each block's plaintext size to avoid a sizing retry.
+ * ZPAQGPU_E_NOSPACE sets *out_need / *n_segs to what is required. */
+int zpaqgpu_decompress_archive(zpaqgpu_ctx *ctx, const uint8_t *arc, uint64_t len, uint8_t *out,
+                               uint64_t out_cap, uint64_t *out_need, zpaqgpu_segment *segs,
+                               int segs_cap, int *n_segs);
+/* Device-resident variant for single-segment blocks laid out back to back (what
+ * zpaqgpu_compress_blocks_dev produced): block k occupies [h_arc_off[k], h_arc_off[k+1]) of
+ * d_arc and its plaintext goes to d_out + h_out_off[k] (capacity h_out_off[k+1]-h_out_off[k]).
+ * d_out_len (device, n_blocks x uint64) receives each block's plaintext size; *n_bad counts
+ * blocks whose SHA1 or framing failed. */
+int zpaqgpu_decompress_blocks_dev(zpaqgpu_ctx *ctx, const void *d_arc, const uint64_t *h_arc_off,
+                                  int n_blocks, void *d_out, const uint64_t *h_out_off,
+                                  void *d_out_len, int *n_bad);
+
+/* ---- streaming-shaped calls (what the V shim's methods map to) -------------------------- */
+/* Compressor.start_block(level) (compressor.v:79).  Data is buffered on the host and the block
+ * is coded on the device at block_end; byte output equals the reference's. */
+int zpaqgpu_block_begin(zpaqgpu_ctx *ctx, int level);
+int zpaqgpu_block_begin_header(zpaqgpu_ctx *ctx, const uint8_t *header, int header_len);
+/* Compressor.start_segment(filename, comment) (compressor.v:212) */
+int zpaqgpu_segment_begin(zpaqgpu_ctx *ctx, const char *filename, const char *comment);
+/* Compressor.compress(n) (compressor.v:259): the shim drains its Reader and passes the bytes.
+ * A call with len == 0 still counts as "compress was called" (the PP byte). */
+int zpaqgpu_segment_write(zpaqgpu_ctx *ctx, const uint8_t *data, uint64_t len);
+/* Compressor.end_segment() (compressor.v:357) */
+int zpaqgpu_segment_end(zpaqgpu_ctx *ctx);
+/* Compressor.end_block() (compressor.v:402): returns the block's byte count (>=0) written to out,
+ * or ZPAQGPU_E_NOSPACE with *need set (call again with a larger buffer; the block is kept). */
+int64_t zpaqgpu_block_end(zpaqgpu_ctx *ctx, uint8_t *out, uint64_t cap, uint64_t *need);
+
+/* ---- measurement ------------------------------------------------------------------------ */
+typedef struct {
+    float init_ms;     /* table zero/fill kernels                      */
+    float codec_ms;    /* k_encode_* / k_decode_* (the dominant kernel) */
+    float sha1_ms;     /* k_sha1_segments                              */
+    float pack_ms;     /* k_scan_sizes + k_pack_blocks / find_blocks   */
+    float h2d_ms, d2h_ms;
+    int32_t launches;  /* kernels launched by the last call            */
+    int32_t codec_launches;
+    int32_t waves;     /* table-memory waves the batch was split into  */
+    int32_t retries;   /* output-sizing retries                        */
+    int32_t kernel;    /* ZPAQGPU_KERNEL_GENERIC or _CHAIN actually used */
+    int32_t warps_per_cta;
+    uint64_t workspace_bytes_per_block;
+} zpaqgpu_stats;
+int zpaqgpu_last_stats(const zpaqgpu_ctx *ctx, zpaqgpu_stats *out);
+
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
+#ifdef __cplusplus
+}
+#endif
+#endif

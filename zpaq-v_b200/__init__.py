@@ -1,0 +1,13 @@
+"""zpaq-v_b200: B200-native ZPAQ block codec behind the dy-tea/zpaq-v Compressor/Decompresser API.
+
+csrc/      CUDA kernels (sm_100a) and the C ABI (include/zpaqgpu.h) -> libzpaqgpu.so
+binding.py ctypes marshalling of the C ABI
+codec.py   host mirror of the reference's Compressor / Decompresser / Reader / Writer
+vshim/     the V-side binding a maintainer of the reference would add (not compilable here)
+"""
+from . import binding
+from .binding import Context, ZpaqGpuError, level_header, tables
+from .codec import Compressor, Decompresser, FileReader, FileWriter
+
+__all__ = ["binding", "Context", "ZpaqGpuError", "level_header", "tables", "Compressor", "Decompresser",
+           "FileReader", "FileWriter"]

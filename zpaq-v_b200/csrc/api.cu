@@ -1,0 +1,1133 @@
+// api.cu -- the C ABI of libzpaqgpu (include/zpaqgpu.h): context, device-buffer management,
+// wave scheduling over the table workspace and the host side of block framing.
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/zpaqgpu.h"
+#include "common.cuh"
+#include "kernels.h"
+#include "model.h"
+
+using namespace zg;
+
+namespace {
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+};
+
+struct PendingSeg {
+    std::string name, comment;
+    std::vector<uint8_t> data;
+    bool called = false;  // compress() was called at least once
+};
+
+struct SegSpec {  // one segment of a compression job
+    const char *name, *comment;
+    u64 in_off, in_len;
+    bool called;
+};
+
+}  // namespace
+
+struct zpaqgpu_ctx {
+    int device = 0;
+    cudaStream_t own_stream = nullptr, stream = nullptr, side_stream = nullptr;
+    cudaEvent_t ev[8] = {};
+    cudaEvent_t ev_side = nullptr, ev_main = nullptr;
+    DevTables tables{};
+    void *tables_mem = nullptr;
+    int kernel_pref = ZPAQGPU_KERNEL_AUTO;
+    u64 ws_limit = 0;
+    int sm_count = 148;
+    std::string err;
+    zpaqgpu_stats stats{};
+    // grow-only device buffers
+    DevBuf workspace, in, arena, out, desc, pay_len, digests, seg_size, out_off, modelblob, results,
+        seg_recs, misc, heads, plain;
+    // pinned host staging for small read-backs
+    void *pinned = nullptr;
+    size_t pinned_cap = 0;
+    // streaming-shaped state (compressor.v:6-8 state machine)
+    int st_state = 2;  // 0 block, 1 segment, 2 start
+    Model st_model;
+    std::vector<PendingSeg> st_segs;
+    std::vector<uint8_t> st_done;  // finished block kept until the caller's buffer is large enough
+    bool st_has_done = false;
+};
+
+namespace {
+
+#define CK(call)                                                                              \
+    do {                                                                                      \
+        cudaError_t e_ = (call);                                                              \
+        if (e_ != cudaSuccess) {                                                              \
+            ctx->err = std::string(#call) + ": " + cudaGetErrorString(e_);                    \
+            return ZPAQGPU_E_CUDA;                                                            \
+        }                                                                                     \
+    } while (0)
+
+int ensure(zpaqgpu_ctx *ctx, DevBuf &b, size_t bytes) {
+    if (bytes <= b.cap) return ZPAQGPU_OK;
+    if (b.p) {
+        CK(cudaStreamSynchronize(ctx->stream));
+        CK(cudaFree(b.p));
+        b.p = nullptr, b.cap = 0;
+    }
+    size_t want = bytes + bytes / 8 + 4096;
+    cudaError_t e = cudaMalloc(&b.p, want);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        want = bytes;
+        e = cudaMalloc(&b.p, want);
+    }
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        ctx->err = "cudaMalloc of " + std::to_string(bytes) + " bytes failed";
+        return ZPAQGPU_E_NOMEM;
+    }
+    b.cap = want;
+    return ZPAQGPU_OK;
+}
+
+int ensure_pinned(zpaqgpu_ctx *ctx, size_t bytes) {
+    if (bytes <= ctx->pinned_cap) return ZPAQGPU_OK;
+    if (ctx->pinned) cudaFreeHost(ctx->pinned);
+    ctx->pinned = nullptr, ctx->pinned_cap = 0;
+    CK(cudaMallocHost(&ctx->pinned, bytes + 4096));
+    ctx->pinned_cap = bytes + 4096;
+    return ZPAQGPU_OK;
+}
+
+u64 align_up(u64 v, u64 a) { return (v + a - 1) / a * a; }
+
+// Upload the model (header bytes + component table) and return the device view.
+int upload_model(zpaqgpu_ctx *ctx, const Model &m, ModelDev &md, const FillRegion **d_fills,
+                 const u32 **d_image) {
+    const size_t hdr_bytes = align_up(m.header.size() + 1, 16);
+    const size_t comp_bytes = align_up(sizeof(CompDesc) * std::max<size_t>(1, m.comps.size()), 16);
+    const size_t fill_bytes = align_up(sizeof(FillRegion) * std::max<size_t>(1, m.fills.size()), 16);
+    const size_t img_bytes = align_up(4 * std::max<size_t>(1, m.image.size()), 16);
+    const size_t total = hdr_bytes + comp_bytes + fill_bytes + img_bytes;
+    int rc = ensure(ctx, ctx->modelblob, total);
+    if (rc) return rc;
+    std::vector<uint8_t> blob(total, 0);
+    std::memcpy(blob.data(), m.header.data(), m.header.size());
+    if (!m.comps.empty()) std::memcpy(blob.data() + hdr_bytes, m.comps.data(), sizeof(CompDesc) * m.comps.size());
+    if (!m.fills.empty())
+        std::memcpy(blob.data() + hdr_bytes + comp_bytes, m.fills.data(), sizeof(FillRegion) * m.fills.size());
+    if (!m.image.empty())
+        std::memcpy(blob.data() + hdr_bytes + comp_bytes + fill_bytes, m.image.data(), 4 * m.image.size());
+    // the blob of the previous launch may still be in use by queued kernels
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaMemcpyAsync(ctx->modelblob.p, blob.data(), total, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    u8 *base = static_cast<u8 *>(ctx->modelblob.p);
+    md.n = m.n, md.cend = m.cend, md.hbegin = m.hbegin, md.hend = m.hend, md.header_len = int(m.header.size());
+    md.h_len = m.h_len, md.m_len = m.m_len;
+    md.h_off = m.h_off, md.m_off = m.m_off, md.r_off = m.r_off, md.rt_off = m.rt_off;
+    md.ws_bytes = m.ws_bytes;
+    md.header = base;
+    md.comps = reinterpret_cast<const CompDesc *>(base + hdr_bytes);
+    md.ctx_mode = m.ctx_mode, md.n_hash = m.n_hash;
+    *d_fills = reinterpret_cast<const FillRegion *>(base + hdr_bytes + comp_bytes);
+    *d_image = reinterpret_cast<const u32 *>(base + hdr_bytes + comp_bytes + fill_bytes);
+    return ZPAQGPU_OK;
+}
+
+// How many blocks can have their tables resident at once.
+int plan_slots(zpaqgpu_ctx *ctx, const Model &m, int n_blocks, size_t other_bytes, int *slots) {
+    size_t free_b = 0, total_b = 0;
+    CK(cudaMemGetInfo(&free_b, &total_b));
+    free_b += ctx->workspace.cap;  // our own cached workspace can be reused
+    u64 budget = ctx->ws_limit ? ctx->ws_limit : u64(double(free_b) * 0.80);
+    if (!ctx->ws_limit && budget > other_bytes) budget -= std::min<u64>(other_bytes, budget / 2);
+    u64 n = m.ws_bytes ? budget / m.ws_bytes : u64(n_blocks);
+    if (n < 1) {
+        ctx->err = "model tables (" + std::to_string(m.ws_bytes) + " bytes per block) exceed the workspace budget";
+        return ZPAQGPU_E_NOMEM;
+    }
+    *slots = int(std::min<u64>(n, u64(n_blocks)));
+    return ZPAQGPU_OK;
+}
+
+bool use_chain(const zpaqgpu_ctx *ctx, const Model &m) {
+    if (ctx->kernel_pref == ZPAQGPU_KERNEL_GENERIC) return false;
+    return m.is_chain;
+}
+
+int pick_warps_per_cta(const zpaqgpu_ctx *ctx, const Model &m, int n_resident) {
+    const int wmax = chain_max_warps_per_cta(m);
+    int w = (n_resident + ctx->sm_count - 1) / ctx->sm_count;
+    return std::max(1, std::min(wmax, w));
+}
+
+float elapsed(cudaEvent_t a, cudaEvent_t b) {
+    float ms = 0;
+    cudaEventElapsedTime(&ms, a, b);
+    return ms;
+}
+
+// ------------------------------------------------------------------------------------------
+// Compression job: blocks of segments, plaintext already on the device.
+// ------------------------------------------------------------------------------------------
+struct CompressJob {
+    const Model *model;
+    std::vector<EncBlock> blocks;
+    std::vector<SegSpec> segs;
+    const u8 *d_in;       // plaintext on the device
+    u8 *d_out;            // where the archive bytes go (device)
+    u64 out_cap;
+    u64 *d_out_off;       // device, n_blocks+1
+    // results
+    u64 total = 0;
+    bool fits = true;
+};
+
+int run_compress(zpaqgpu_ctx *ctx, CompressJob &job) {
+    const Model &m = *job.model;
+    const int n_blocks = int(job.blocks.size()), n_segs = int(job.segs.size());
+    ctx->stats = zpaqgpu_stats{};
+    ctx->stats.workspace_bytes_per_block = m.ws_bytes;
+    const bool store = m.n == 0;
+    const bool chain = !store && use_chain(ctx, m);
+    if (!store && ctx->kernel_pref == ZPAQGPU_KERNEL_CHAIN && !m.is_chain) {
+        ctx->err = "model does not have the ICM/ISSE-chain shape";
+        return ZPAQGPU_E_UNSUPPORTED;
+    }
+    ctx->stats.kernel = store ? 0 : (chain ? ZPAQGPU_KERNEL_CHAIN : ZPAQGPU_KERNEL_GENERIC);
+    cudaStream_t st = ctx->stream;
+
+    // framing bytes in front of each payload (compressor.v:150-181, :217-235)
+    std::vector<uint8_t> pre;
+    std::vector<PackSeg> pack(static_cast<size_t>(n_segs));
+    std::vector<EncSeg> esegs(static_cast<size_t>(n_segs));
+    std::vector<ShaJob> sha(static_cast<size_t>(n_segs));
+    std::vector<u64> caps(static_cast<size_t>(n_segs), 0);
+    for (int attempt = 0; attempt < 3; ++attempt) {
+        pre.clear();
+        u64 arena_bytes = 0;
+        for (int b = 0; b < n_blocks; ++b) {
+            const EncBlock &blk = job.blocks[size_t(b)];
+            for (u32 k = 0; k < blk.n_seg; ++k) {
+                const u32 s = blk.first_seg + k;
+                const SegSpec &sp = job.segs[s];
+                PackSeg &ps = pack[s];
+                ps.pre_off = pre.size();
+                if (k == 0) pre.insert(pre.end(), m.block_prefix.begin(), m.block_prefix.end());
+                pre.push_back(1);
+                for (const char *c = sp.name ? sp.name : ""; *c; ++c) pre.push_back(uint8_t(*c));
+                pre.push_back(0);
+                for (const char *c = sp.comment ? sp.comment : ""; *c; ++c) pre.push_back(uint8_t(*c));
+                pre.push_back(0);
+                pre.push_back(0);
+                ps.pre_len = u32(pre.size() - ps.pre_off);
+                ps.store = store ? 1 : 0;
+                ps.in_off = sp.in_off, ps.in_len = sp.in_len;
+                ps.flags = sp.called ? 1u : 0u;
+                ps.last = (k + 1 == blk.n_seg) ? 1 : 0;
+                if (attempt == 0) caps[s] = store ? 0 : sp.in_len + sp.in_len / 8 + 512;
+                ps.pay_off = arena_bytes, ps.pay_cap = caps[s];
+                arena_bytes += align_up(caps[s], 256);
+                EncSeg &es = esegs[s];
+                es.in_off = sp.in_off, es.in_len = sp.in_len, es.pay_off = ps.pay_off, es.pay_cap = caps[s];
+                es.flags = ps.flags, es.pad = 0;
+                sha[s].off = sp.in_off, sha[s].len = sp.in_len;
+            }
+        }
+        // descriptor blob
+        const size_t o_blocks = 0;
+        const size_t o_esegs = align_up(o_blocks + sizeof(EncBlock) * size_t(n_blocks), 16);
+        const size_t o_pack = align_up(o_esegs + sizeof(EncSeg) * size_t(n_segs), 16);
+        const size_t o_sha = align_up(o_pack + sizeof(PackSeg) * size_t(n_segs), 16);
+        const size_t o_pre = align_up(o_sha + sizeof(ShaJob) * size_t(n_segs), 16);
+        const size_t desc_bytes = align_up(o_pre + pre.size() + 16, 16);
+        int rc;
+        if ((rc = ensure(ctx, ctx->desc, desc_bytes))) return rc;
+        if ((rc = ensure(ctx, ctx->arena, std::max<u64>(arena_bytes, 256)))) return rc;
+        if ((rc = ensure(ctx, ctx->pay_len, 8 * size_t(n_segs) + 16))) return rc;
+        if ((rc = ensure(ctx, ctx->digests, 20 * size_t(n_segs) + 16))) return rc;
+        if ((rc = ensure(ctx, ctx->seg_size, 8 * size_t(n_segs) + 16))) return rc;
+        std::vector<uint8_t> blob(desc_bytes, 0);
+        std::memcpy(blob.data() + o_blocks, job.blocks.data(), sizeof(EncBlock) * size_t(n_blocks));
+        std::memcpy(blob.data() + o_esegs, esegs.data(), sizeof(EncSeg) * size_t(n_segs));
+        std::memcpy(blob.data() + o_pack, pack.data(), sizeof(PackSeg) * size_t(n_segs));
+        std::memcpy(blob.data() + o_sha, sha.data(), sizeof(ShaJob) * size_t(n_segs));
+        if (!pre.empty()) std::memcpy(blob.data() + o_pre, pre.data(), pre.size());
+        CK(cudaMemcpyAsync(ctx->desc.p, blob.data(), desc_bytes, cudaMemcpyHostToDevice, st));
+        CK(cudaStreamSynchronize(st));  // blob is a stack-lifetime host buffer
+        u8 *dbase = static_cast<u8 *>(ctx->desc.p);
+        const EncBlock *d_blocks = reinterpret_cast<const EncBlock *>(dbase + o_blocks);
+        const EncSeg *d_esegs = reinterpret_cast<const EncSeg *>(dbase + o_esegs);
+        const PackSeg *d_pack = reinterpret_cast<const PackSeg *>(dbase + o_pack);
+        const ShaJob *d_sha = reinterpret_cast<const ShaJob *>(dbase + o_sha);
+        const u8 *d_pre = dbase + o_pre;
+
+        // SHA-1 of the plaintext runs beside the codec on the side stream (compressor.v:284)
+        CK(cudaEventRecord(ctx->ev_main, st));
+        CK(cudaStreamWaitEvent(ctx->side_stream, ctx->ev_main, 0));
+        CK(cudaEventRecord(ctx->ev[4], ctx->side_stream));
+        launch_sha1(job.d_in, d_sha, n_segs, static_cast<u8 *>(ctx->digests.p), ctx->side_stream);
+        CK(cudaEventRecord(ctx->ev[5], ctx->side_stream));
+        CK(cudaEventRecord(ctx->ev_side, ctx->side_stream));
+        ctx->stats.launches += 1;
+
+        float init_ms = 0, codec_ms = 0;
+        if (!store) {
+            ModelDev md;
+            const FillRegion *d_fills;
+            const u32 *d_image;
+            if ((rc = upload_model(ctx, m, md, &d_fills, &d_image))) return rc;
+            int slots = 0;
+            if ((rc = plan_slots(ctx, m, n_blocks, arena_bytes, &slots))) return rc;
+            if ((rc = ensure(ctx, ctx->workspace, u64(slots) * m.ws_bytes))) return rc;
+            const int wpc = chain ? pick_warps_per_cta(ctx, m, slots) : 4;
+            ctx->stats.warps_per_cta = wpc;
+            for (int first = 0; first < n_blocks; first += slots) {
+                const int n = std::min(slots, n_blocks - first);
+                CK(cudaEventRecord(ctx->ev[0], st));
+                CK(cudaMemsetAsync(ctx->workspace.p, 0, u64(n) * m.ws_bytes, st));
+                FillArgs fa{static_cast<u8 *>(ctx->workspace.p), m.ws_bytes, n, d_fills, int(m.fills.size()), d_image};
+                launch_fill(fa, st);
+                CK(cudaEventRecord(ctx->ev[1], st));
+                EncodeArgs ea;
+                ea.model = md, ea.tables = ctx->tables;
+                ea.workspace = static_cast<u8 *>(ctx->workspace.p);
+                ea.in = job.d_in, ea.arena = static_cast<u8 *>(ctx->arena.p);
+                ea.blocks = d_blocks, ea.segs = d_esegs, ea.pay_len = static_cast<u64 *>(ctx->pay_len.p);
+                ea.first_block = first, ea.n_blocks = n;
+                if (chain) {
+                    if (!launch_encode_chain(m, ea, wpc, st)) {
+                        ctx->err = "no chain kernel instantiation for this model";
+                        return ZPAQGPU_E_UNSUPPORTED;
+                    }
+                } else {
+                    k_encode_generic<<<(n + 3) / 4, 128, 0, st>>>(ea);
+                }
+                CK(cudaGetLastError());
+                CK(cudaEventRecord(ctx->ev[2], st));
+                CK(cudaEventSynchronize(ctx->ev[2]));
+                init_ms += elapsed(ctx->ev[0], ctx->ev[1]);
+                codec_ms += elapsed(ctx->ev[1], ctx->ev[2]);
+                ctx->stats.launches += 2 + (m.fills.empty() ? 0 : 1);
+                ctx->stats.codec_launches += 1;
+                ctx->stats.waves += 1;
+            }
+        }
+        ctx->stats.init_ms += init_ms, ctx->stats.codec_ms += codec_ms;
+        // assemble: [prefix][payload][00000000 FD sha1][FF] per segment (compressor.v:380-395, :409)
+        CK(cudaStreamWaitEvent(st, ctx->ev_side, 0));
+        CK(cudaEventRecord(ctx->ev[2], st));
+        PackArgs pa;
+        pa.segs = d_pack, pa.blocks = d_blocks, pa.n_blocks = n_blocks, pa.pre = d_pre, pa.in = job.d_in;
+        pa.arena = static_cast<const u8 *>(ctx->arena.p), pa.pay_len = static_cast<const u64 *>(ctx->pay_len.p);
+        pa.digests = static_cast<const u8 *>(ctx->digests.p), pa.seg_size = static_cast<u64 *>(ctx->seg_size.p);
+        pa.out_off = job.d_out_off, pa.out = job.d_out, pa.out_cap = job.out_cap;
+        launch_pack(pa, n_segs, st);
+        CK(cudaGetLastError());
+        CK(cudaEventRecord(ctx->ev[3], st));
+        ctx->stats.launches += 3;
+        // read back the total and the payload sizes to detect slot overflow
+        if ((rc = ensure_pinned(ctx, 8 * size_t(n_segs) + 64))) return rc;
+        u64 *h_total = static_cast<u64 *>(ctx->pinned);
+        u64 *h_pay = h_total + 1;
+        CK(cudaMemcpyAsync(h_total, job.d_out_off + n_blocks, 8, cudaMemcpyDeviceToHost, st));
+        if (!store) CK(cudaMemcpyAsync(h_pay, ctx->pay_len.p, 8 * size_t(n_segs), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        ctx->stats.pack_ms += elapsed(ctx->ev[2], ctx->ev[3]);
+        ctx->stats.sha1_ms += elapsed(ctx->ev[4], ctx->ev[5]);
+        bool overflow = false;
+        if (!store)
+            for (int s = 0; s < n_segs; ++s)
+                if (h_pay[s] > caps[size_t(s)]) caps[size_t(s)] = h_pay[s] + 64, overflow = true;
+        if (!overflow) {
+            job.total = *h_total;
+            job.fits = job.total <= job.out_cap;
+            return ZPAQGPU_OK;
+        }
+        ctx->stats.retries += 1;
+    }
+    ctx->err = "payload slot sizing did not converge";
+    return ZPAQGPU_E_CUDA;
+}
+
+std::string size_comment(u64 n) { return std::to_string(n) + " bytes"; }
+
+int compress_host(zpaqgpu_ctx *ctx, const Model &m, const uint8_t *in, const uint64_t *in_off, int n_blocks,
+                  const char *const *names, const char *const *comments, uint8_t *out, uint64_t out_cap,
+                  uint64_t *out_off, uint64_t *out_need) {
+    if (!ctx || n_blocks < 0 || (n_blocks > 0 && (!in_off || !out_off))) return ZPAQGPU_E_ARG;
+    if (n_blocks == 0) {
+        if (out_off) out_off[0] = 0;
+        if (out_need) *out_need = 0;
+        return ZPAQGPU_OK;
+    }
+    CK(cudaSetDevice(ctx->device));
+    const u64 base = in_off[0], total_in = in_off[n_blocks] - base;
+    if (total_in > 0 && !in) return ZPAQGPU_E_ARG;
+    cudaStream_t st = ctx->stream;
+    int rc;
+    if ((rc = ensure(ctx, ctx->in, std::max<u64>(total_in, 16)))) return rc;
+    CK(cudaEventRecord(ctx->ev[6], st));
+    if (total_in) CK(cudaMemcpyAsync(ctx->in.p, in + base, total_in, cudaMemcpyHostToDevice, st));
+    CK(cudaEventRecord(ctx->ev[7], st));
+    CompressJob job;
+    job.model = &m;
+    job.blocks.resize(size_t(n_blocks));
+    job.segs.resize(size_t(n_blocks));
+    u64 worst = 0;
+    for (int b = 0; b < n_blocks; ++b) {
+        if (in_off[b + 1] < in_off[b]) return ZPAQGPU_E_ARG;
+        job.blocks[size_t(b)] = EncBlock{u32(b), 1};
+        SegSpec &sp = job.segs[size_t(b)];
+        sp.name = names ? names[b] : nullptr;
+        sp.comment = comments ? comments[b] : nullptr;
+        sp.in_off = in_off[b] - base, sp.in_len = in_off[b + 1] - in_off[b];
+        sp.called = true;  // cmd/main.v:305 always calls compress() at least once
+        worst += sp.in_len + sp.in_len / 4 + 2048 + std::strlen(sp.name ? sp.name : "") +
+                 std::strlen(sp.comment ? sp.comment : "");
+    }
+    // the assembled archive is produced on the device and copied out in one piece
+    const u64 dcap = worst;
+    if ((rc = ensure(ctx, ctx->out, dcap))) return rc;
+    if ((rc = ensure(ctx, ctx->out_off, 8 * size_t(n_blocks + 1)))) return rc;
+    job.d_in = static_cast<const u8 *>(ctx->in.p);
+    job.d_out = static_cast<u8 *>(ctx->out.p), job.out_cap = ctx->out.cap;
+    job.d_out_off = static_cast<u64 *>(ctx->out_off.p);
+    if ((rc = run_compress(ctx, job))) return rc;
+    ctx->stats.h2d_ms = elapsed(ctx->ev[6], ctx->ev[7]);
+    if (!job.fits) {
+        // the device buffer was sized from a worst-case guess; grow it and assemble again
+        if ((rc = ensure(ctx, ctx->out, job.total))) return rc;
+        job.d_out = static_cast<u8 *>(ctx->out.p), job.out_cap = ctx->out.cap;
+        if ((rc = run_compress(ctx, job))) return rc;
+    }
+    if (out_need) *out_need = job.total;
+    CK(cudaMemcpyAsync(out_off, ctx->out_off.p, 8 * size_t(n_blocks + 1), cudaMemcpyDeviceToHost, st));
+    if (job.total > out_cap) {
+        CK(cudaStreamSynchronize(st));
+        return ZPAQGPU_E_NOSPACE;
+    }
+    if (job.total && !out) return ZPAQGPU_E_ARG;
+    CK(cudaEventRecord(ctx->ev[6], st));
+    if (job.total) CK(cudaMemcpyAsync(out, ctx->out.p, job.total, cudaMemcpyDeviceToHost, st));
+    CK(cudaEventRecord(ctx->ev[7], st));
+    CK(cudaStreamSynchronize(st));
+    ctx->stats.d2h_ms = elapsed(ctx->ev[6], ctx->ev[7]);
+    return ZPAQGPU_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// Decompression job over an archive resident on the device.
+// ------------------------------------------------------------------------------------------
+struct DecCandidate {
+    u64 start;       // offset of the level byte (just after the locator)
+    u64 payload;     // offset of the first segment marker
+    int group = -1;  // index into models, -1: header rejected
+    u64 hint = 0;    // plaintext capacity to reserve
+    u64 out_off = 0;
+    DecBlockOut res{};
+};
+
+struct DecompressJob {
+    const u8 *d_arc;
+    u64 arc_len;
+    std::vector<DecCandidate> cand;
+    std::vector<Model> models;
+    u8 *d_plain;     // plaintext arena on the device
+    std::vector<DecSegRec> recs;   // sorted by (block, index)
+    std::vector<i32> sha_ok;       // parallel to recs
+};
+
+int run_decompress(zpaqgpu_ctx *ctx, DecompressJob &job, bool caller_owns_plain) {
+    cudaStream_t st = ctx->stream;
+    const int n = int(job.cand.size());
+    ctx->stats = zpaqgpu_stats{};
+    int rc;
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        // plaintext slots, back to back in candidate order
+        u64 plain_bytes = 0;
+        std::vector<DecBlock> blocks(static_cast<size_t>(n));
+        for (int i = 0; i < n; ++i) {
+            DecCandidate &c = job.cand[size_t(i)];
+            if (!caller_owns_plain) c.out_off = plain_bytes;
+            blocks[size_t(i)] = DecBlock{c.payload, c.out_off, c.hint};
+            plain_bytes += c.hint;
+        }
+        if (!caller_owns_plain) {
+            if ((rc = ensure(ctx, ctx->plain, std::max<u64>(plain_bytes, 16)))) return rc;
+            job.d_plain = static_cast<u8 *>(ctx->plain.p);
+        }
+        u32 seg_cap = u32(std::max(64, n * 2 + 64));
+        for (int seg_try = 0; seg_try < 2; ++seg_try) {
+            if ((rc = ensure(ctx, ctx->desc, sizeof(DecBlock) * size_t(n) + 16))) return rc;
+            if ((rc = ensure(ctx, ctx->results, sizeof(DecBlockOut) * size_t(n) + 16))) return rc;
+            if ((rc = ensure(ctx, ctx->seg_recs, sizeof(DecSegRec) * size_t(seg_cap) + 16))) return rc;
+            if ((rc = ensure(ctx, ctx->misc, 64))) return rc;
+            CK(cudaMemcpyAsync(ctx->desc.p, blocks.data(), sizeof(DecBlock) * size_t(n), cudaMemcpyHostToDevice, st));
+            CK(cudaMemsetAsync(ctx->misc.p, 0, 64, st));
+            CK(cudaMemsetAsync(ctx->results.p, 0, sizeof(DecBlockOut) * size_t(n), st));
+            CK(cudaStreamSynchronize(st));
+            // one launch group per distinct model; candidates of a group are contiguous runs
+            for (size_t g = 0; g < job.models.size(); ++g) {
+                const Model &m = job.models[g];
+                ctx->stats.workspace_bytes_per_block = m.ws_bytes;
+                ModelDev md;
+                const FillRegion *d_fills;
+                const u32 *d_image;
+                if ((rc = upload_model(ctx, m, md, &d_fills, &d_image))) return rc;
+                const bool store = m.n == 0;
+                const bool chain = !store && use_chain(ctx, m);
+                if (!store && ctx->kernel_pref == ZPAQGPU_KERNEL_CHAIN && !m.is_chain) {
+                    ctx->err = "model does not have the ICM/ISSE-chain shape";
+                    return ZPAQGPU_E_UNSUPPORTED;
+                }
+                if (!store) ctx->stats.kernel = chain ? ZPAQGPU_KERNEL_CHAIN : ZPAQGPU_KERNEL_GENERIC;
+                int i = 0;
+                while (i < n) {
+                    if (job.cand[size_t(i)].group != int(g)) { ++i; continue; }
+                    int j = i;
+                    while (j < n && job.cand[size_t(j)].group == int(g)) ++j;
+                    const int run = j - i;
+                    int slots = run;
+                    if (!store) {
+                        if ((rc = plan_slots(ctx, m, run, plain_bytes, &slots))) return rc;
+                        if ((rc = ensure(ctx, ctx->workspace, u64(slots) * m.ws_bytes))) return rc;
+                    }
+                    const int wpc = chain ? pick_warps_per_cta(ctx, m, slots) : 4;
+                    ctx->stats.warps_per_cta = wpc;
+                    for (int first = i; first < j; first += slots) {
+                        const int cnt = std::min(slots, j - first);
+                        DecodeArgs da;
+                        da.model = md, da.tables = ctx->tables;
+                        da.workspace = static_cast<u8 *>(ctx->workspace.p);
+                        da.arc = job.d_arc, da.arc_len = job.arc_len, da.out = job.d_plain;
+                        da.blocks = static_cast<const DecBlock *>(ctx->desc.p);
+                        da.results = static_cast<DecBlockOut *>(ctx->results.p);
+                        da.seg_recs = static_cast<DecSegRec *>(ctx->seg_recs.p);
+                        da.seg_count = static_cast<u32 *>(ctx->misc.p);
+                        da.seg_cap = seg_cap, da.first_block = first, da.n_blocks = cnt;
+                        CK(cudaEventRecord(ctx->ev[0], st));
+                        if (store) {
+                            CK(cudaEventRecord(ctx->ev[1], st));
+                            launch_decode_store(da, st);
+                        } else {
+                            CK(cudaMemsetAsync(ctx->workspace.p, 0, u64(cnt) * m.ws_bytes, st));
+                            FillArgs fa{static_cast<u8 *>(ctx->workspace.p), m.ws_bytes, cnt, d_fills,
+                                        int(m.fills.size()), d_image};
+                            launch_fill(fa, st);
+                            CK(cudaEventRecord(ctx->ev[1], st));
+                            if (chain) {
+                                if (!launch_decode_chain(m, da, wpc, st)) {
+                                    ctx->err = "no chain kernel instantiation for this model";
+                                    return ZPAQGPU_E_UNSUPPORTED;
+                                }
+                            } else {
+                                k_decode_generic<<<(cnt + 3) / 4, 128, 0, st>>>(da);
+                            }
+                            ctx->stats.launches += 1 + (m.fills.empty() ? 0 : 1);
+                        }
+                        CK(cudaGetLastError());
+                        CK(cudaEventRecord(ctx->ev[2], st));
+                        CK(cudaEventSynchronize(ctx->ev[2]));
+                        ctx->stats.init_ms += elapsed(ctx->ev[0], ctx->ev[1]);
+                        ctx->stats.codec_ms += elapsed(ctx->ev[1], ctx->ev[2]);
+                        ctx->stats.launches += 1;
+                        ctx->stats.codec_launches += 1;
+                        ctx->stats.waves += 1;
+                    }
+                    i = j;
+                }
+            }
+            // results
+            if ((rc = ensure_pinned(ctx, sizeof(DecBlockOut) * size_t(n) + 64))) return rc;
+            u32 *h_count = static_cast<u32 *>(ctx->pinned);
+            DecBlockOut *h_res = reinterpret_cast<DecBlockOut *>(static_cast<u8 *>(ctx->pinned) + 64);
+            CK(cudaMemcpyAsync(h_count, ctx->misc.p, 4, cudaMemcpyDeviceToHost, st));
+            CK(cudaMemcpyAsync(h_res, ctx->results.p, sizeof(DecBlockOut) * size_t(n), cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            const u32 count = *h_count;
+            for (int i = 0; i < n; ++i) job.cand[size_t(i)].res = h_res[i];
+            if (count > seg_cap) {  // more segments than record slots: run again with room for all
+                seg_cap = count + 64;
+                ctx->stats.retries += 1;
+                continue;
+            }
+            job.recs.resize(count);
+            if (count) {
+                CK(cudaMemcpy(job.recs.data(), ctx->seg_recs.p, sizeof(DecSegRec) * size_t(count), cudaMemcpyDeviceToHost));
+            }
+            break;
+        }
+        bool overflow = false;
+        for (int i = 0; i < n; ++i) {
+            DecCandidate &c = job.cand[size_t(i)];
+            if (c.group >= 0 && c.res.out_len > c.hint) {
+                if (caller_owns_plain) {
+                    ctx->err = "block " + std::to_string(i) + " decodes to " + std::to_string(c.res.out_len) +
+                               " bytes, more than its output slot";
+                    return ZPAQGPU_E_NOSPACE;
+                }
+                overflow = true;
+            }
+            if (c.group >= 0) c.hint = std::max<u64>(c.res.out_len, 1);
+        }
+        if (!overflow) break;
+        if (attempt == 1) {
+            ctx->err = "plaintext slot sizing did not converge";
+            return ZPAQGPU_E_CUDA;
+        }
+        ctx->stats.retries += 1;
+    }
+    std::sort(job.recs.begin(), job.recs.end(), [](const DecSegRec &a, const DecSegRec &b) {
+        return a.block != b.block ? a.block < b.block : a.index < b.index;
+    });
+    // SHA-1 of every segment's plaintext against the stored digest (decompressor.v:608-628)
+    const int ns = int(job.recs.size());
+    job.sha_ok.assign(size_t(ns), -1);
+    if (ns) {
+        std::vector<ShaJob> jobs(static_cast<size_t>(ns));
+        for (int k = 0; k < ns; ++k) jobs[size_t(k)] = ShaJob{job.recs[size_t(k)].out_off, job.recs[size_t(k)].out_len};
+        if ((rc = ensure(ctx, ctx->seg_size, sizeof(ShaJob) * size_t(ns) + 16))) return rc;
+        if ((rc = ensure(ctx, ctx->digests, 24 * size_t(ns) + 16))) return rc;
+        if ((rc = ensure(ctx, ctx->seg_recs, sizeof(DecSegRec) * size_t(ns) + 16))) return rc;
+        CK(cudaMemcpyAsync(ctx->seg_size.p, jobs.data(), sizeof(ShaJob) * size_t(ns), cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(ctx->seg_recs.p, job.recs.data(), sizeof(DecSegRec) * size_t(ns), cudaMemcpyHostToDevice, st));
+        CK(cudaEventRecord(ctx->ev[4], st));
+        launch_sha1(job.d_plain, static_cast<const ShaJob *>(ctx->seg_size.p), ns, static_cast<u8 *>(ctx->digests.p), st);
+        i32 *d_ok = reinterpret_cast<i32 *>(static_cast<u8 *>(ctx->digests.p) + 20 * size_t(ns));
+        d_ok = reinterpret_cast<i32 *>(align_up(reinterpret_cast<uintptr_t>(d_ok), 4));
+        launch_sha_compare(job.d_arc, job.arc_len, static_cast<const DecSegRec *>(ctx->seg_recs.p), ns,
+                           static_cast<const u8 *>(ctx->digests.p), d_ok, st);
+        CK(cudaEventRecord(ctx->ev[5], st));
+        CK(cudaMemcpyAsync(job.sha_ok.data(), d_ok, 4 * size_t(ns), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        ctx->stats.sha1_ms = elapsed(ctx->ev[4], ctx->ev[5]);
+        ctx->stats.launches += 2;
+    }
+    return ZPAQGPU_OK;
+}
+
+// "<N> bytes" comment convention of cmd/main.v:295-303 as a capacity hint
+u64 comment_hint(const uint8_t *arc, u64 len, u64 payload) {
+    u64 p = payload;
+    if (p >= len || arc[p] != 1) return 0;
+    ++p;
+    while (p < len && arc[p]) ++p;  // filename
+    ++p;
+    u64 v = 0;
+    int digits = 0;
+    while (p < len && arc[p] >= '0' && arc[p] <= '9' && digits < 15) v = v * 10 + (arc[p] - '0'), ++p, ++digits;
+    if (!digits || p + 6 >= len || std::memcmp(arc + p, " bytes", 7) != 0) return 0;
+    return v;
+}
+
+}  // namespace
+
+// ============================================================================================
+// C ABI
+// ============================================================================================
+extern "C" {
+
+const char *zpaqgpu_strerror(int code) {
+    switch (code) {
+    case ZPAQGPU_OK: return "ok";
+    case ZPAQGPU_E_NODEVICE: return "no usable CUDA device (libzpaqgpu has no CPU fallback)";
+    case ZPAQGPU_E_CUDA: return "CUDA error";
+    case ZPAQGPU_E_NOSPACE: return "output buffer too small";
+    case ZPAQGPU_E_ARG: return "bad argument";
+    case ZPAQGPU_E_FORMAT: return "malformed archive";
+    case ZPAQGPU_E_UNSUPPORTED: return "unsupported model or post-processor";
+    case ZPAQGPU_E_STATE: return "call not valid in this state";
+    case ZPAQGPU_E_NOMEM: return "out of device memory";
+    default: return "unknown error";
+    }
+}
+
+int zpaqgpu_init(zpaqgpu_ctx **out, int device) {
+    if (!out) return ZPAQGPU_E_ARG;
+    *out = nullptr;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) {
+        cudaGetLastError();
+        return ZPAQGPU_E_NODEVICE;
+    }
+    if (device < 0 && cudaGetDevice(&device) != cudaSuccess) return ZPAQGPU_E_NODEVICE;
+    if (device >= count) return ZPAQGPU_E_ARG;
+    if (cudaSetDevice(device) != cudaSuccess) return ZPAQGPU_E_NODEVICE;
+    zpaqgpu_ctx *ctx = new zpaqgpu_ctx();
+    ctx->device = device;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->sm_count = prop.multiProcessorCount;
+    bool ok = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaStreamCreateWithFlags(&ctx->side_stream, cudaStreamNonBlocking) == cudaSuccess;
+    ctx->stream = ctx->own_stream;
+    for (auto &e : ctx->ev) ok = ok && cudaEventCreate(&e) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&ctx->ev_side, cudaEventDisableTiming) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&ctx->ev_main, cudaEventDisableTiming) == cudaSuccess;
+    // constant tables: narrowed on the host, uploaded once
+    const Tables &T = tables();
+    const size_t bytes = 32768 * 2 + 4096 * 2 + 512 + 1024 * 4 + 256 * 4;
+    std::vector<uint8_t> img(bytes);
+    int16_t *st = reinterpret_cast<int16_t *>(img.data());
+    uint16_t *sq = reinterpret_cast<uint16_t *>(img.data() + 65536);
+    uint8_t *nx = img.data() + 65536 + 8192;
+    int32_t *dt = reinterpret_cast<int32_t *>(img.data() + 65536 + 8192 + 512);
+    int32_t *d2 = dt + 1024;
+    for (int i = 0; i < 32768; ++i) st[i] = int16_t(T.stretch[i]);
+    for (int i = 0; i < 4096; ++i) sq[i] = uint16_t(T.squash[i]);
+    for (int s = 0; s < 256; ++s) nx[s * 2] = T.ns[s * 4], nx[s * 2 + 1] = T.ns[s * 4 + 1];
+    std::memcpy(dt, T.dt, sizeof(T.dt));
+    std::memcpy(d2, T.dt2k, sizeof(T.dt2k));
+    ok = ok && cudaMalloc(&ctx->tables_mem, bytes) == cudaSuccess;
+    ok = ok && cudaMemcpy(ctx->tables_mem, img.data(), bytes, cudaMemcpyHostToDevice) == cudaSuccess;
+    if (!ok) {
+        cudaGetLastError();
+        zpaqgpu_destroy(ctx);
+        return ZPAQGPU_E_CUDA;
+    }
+    u8 *base = static_cast<u8 *>(ctx->tables_mem);
+    ctx->tables.stretch = reinterpret_cast<const int16_t *>(base);
+    ctx->tables.squash = reinterpret_cast<const u16 *>(base + 65536);
+    ctx->tables.nex = base + 65536 + 8192;
+    ctx->tables.dt = reinterpret_cast<const i32 *>(base + 65536 + 8192 + 512);
+    ctx->tables.dt2k = ctx->tables.dt + 1024;
+    *out = ctx;
+    return ZPAQGPU_OK;
+}
+
+void zpaqgpu_destroy(zpaqgpu_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->own_stream) cudaStreamSynchronize(ctx->own_stream);
+    DevBuf *bufs[] = {&ctx->workspace, &ctx->in, &ctx->arena, &ctx->out, &ctx->desc, &ctx->pay_len,
+                      &ctx->digests, &ctx->seg_size, &ctx->out_off, &ctx->modelblob, &ctx->results,
+                      &ctx->seg_recs, &ctx->misc, &ctx->heads, &ctx->plain};
+    for (DevBuf *b : bufs)
+        if (b->p) cudaFree(b->p);
+    if (ctx->tables_mem) cudaFree(ctx->tables_mem);
+    if (ctx->pinned) cudaFreeHost(ctx->pinned);
+    for (auto &e : ctx->ev)
+        if (e) cudaEventDestroy(e);
+    if (ctx->ev_side) cudaEventDestroy(ctx->ev_side);
+    if (ctx->ev_main) cudaEventDestroy(ctx->ev_main);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+    if (ctx->side_stream) cudaStreamDestroy(ctx->side_stream);
+    delete ctx;
+}
+
+const char *zpaqgpu_last_error(const zpaqgpu_ctx *ctx) { return ctx ? ctx->err.c_str() : ""; }
+
+int zpaqgpu_set_kernel(zpaqgpu_ctx *ctx, int kernel) {
+    if (!ctx || kernel < 0 || kernel > 2) return ZPAQGPU_E_ARG;
+    ctx->kernel_pref = kernel;
+    return ZPAQGPU_OK;
+}
+int zpaqgpu_set_workspace_limit(zpaqgpu_ctx *ctx, uint64_t bytes) {
+    if (!ctx) return ZPAQGPU_E_ARG;
+    ctx->ws_limit = bytes;
+    return ZPAQGPU_OK;
+}
+int zpaqgpu_set_stream(zpaqgpu_ctx *ctx, void *cuda_stream) {
+    if (!ctx) return ZPAQGPU_E_ARG;
+    ctx->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : ctx->own_stream;
+    return ZPAQGPU_OK;
+}
+
+int zpaqgpu_level_header(int level, uint8_t *out, int cap) {
+    const std::vector<uint8_t> h = level_header(level);
+    if (int(h.size()) > cap || !out) return ZPAQGPU_E_NOSPACE;
+    std::memcpy(out, h.data(), h.size());
+    return int(h.size());
+}
+
+int zpaqgpu_tables(int32_t *squash4096, int32_t *stretch32768, uint8_t *state1024) {
+    const Tables &T = tables();
+    if (squash4096) std::memcpy(squash4096, T.squash, sizeof(T.squash));
+    if (stretch32768) std::memcpy(stretch32768, T.stretch, sizeof(T.stretch));
+    if (state1024) std::memcpy(state1024, T.ns, sizeof(T.ns));
+    return ZPAQGPU_OK;
+}
+
+int zpaqgpu_last_stats(const zpaqgpu_ctx *ctx, zpaqgpu_stats *out) {
+    if (!ctx || !out) return ZPAQGPU_E_ARG;
+    *out = ctx->stats;
+    return ZPAQGPU_OK;
+}
+
+// ---- batch compression ----
+int zpaqgpu_compress_blocks_header(zpaqgpu_ctx *ctx, const uint8_t *header, int header_len, const uint8_t *in,
+                                   const uint64_t *in_off, int n_blocks, const char *const *names,
+                                   const char *const *comments, uint8_t *out, uint64_t out_cap,
+                                   uint64_t *out_off, uint64_t *out_need) {
+    if (!ctx) return ZPAQGPU_E_ARG;
+    Model m;
+    const int rc = model_from_level_layout(header, header_len, m);
+    if (rc) {
+        ctx->err = m.error;
+        return rc;
+    }
+    return compress_host(ctx, m, in, in_off, n_blocks, names, comments, out, out_cap, out_off, out_need);
+}
+
+int zpaqgpu_compress_blocks(zpaqgpu_ctx *ctx, int level, const uint8_t *in, const uint64_t *in_off, int n_blocks,
+                            const char *const *names, const char *const *comments, uint8_t *out,
+                            uint64_t out_cap, uint64_t *out_off, uint64_t *out_need) {
+    const std::vector<uint8_t> h = level_header(level);
+    return zpaqgpu_compress_blocks_header(ctx, h.data(), int(h.size()), in, in_off, n_blocks, names, comments,
+                                          out, out_cap, out_off, out_need);
+}
+
+int zpaqgpu_compress_blocks_dev(zpaqgpu_ctx *ctx, int level, const void *d_in, const void *d_in_off,
+                                const uint64_t *h_in_off, int n_blocks, void *d_out, uint64_t out_cap,
+                                void *d_out_off, uint64_t *out_total) {
+    (void)d_in_off;
+    if (!ctx || n_blocks <= 0 || !h_in_off || !d_out || !d_out_off) return ZPAQGPU_E_ARG;
+    CK(cudaSetDevice(ctx->device));
+    const std::vector<uint8_t> h = level_header(level);
+    Model m;
+    int rc = model_from_level_layout(h.data(), int(h.size()), m);
+    if (rc) return ctx->err = m.error, rc;
+    CompressJob job;
+    job.model = &m;
+    job.blocks.resize(size_t(n_blocks));
+    job.segs.resize(size_t(n_blocks));
+    std::vector<std::string> comments(static_cast<size_t>(n_blocks));
+    for (int b = 0; b < n_blocks; ++b) {
+        job.blocks[size_t(b)] = EncBlock{u32(b), 1};
+        SegSpec &sp = job.segs[size_t(b)];
+        sp.in_off = h_in_off[b], sp.in_len = h_in_off[b + 1] - h_in_off[b];
+        comments[size_t(b)] = size_comment(sp.in_len);  // cmd/main.v:303
+        sp.name = "", sp.comment = comments[size_t(b)].c_str();
+        sp.called = true;
+    }
+    job.d_in = static_cast<const u8 *>(d_in);
+    job.d_out = static_cast<u8 *>(d_out), job.out_cap = out_cap;
+    job.d_out_off = static_cast<u64 *>(d_out_off);
+    if ((rc = run_compress(ctx, job))) return rc;
+    if (out_total) *out_total = job.total;
+    return job.fits ? ZPAQGPU_OK : ZPAQGPU_E_NOSPACE;
+}
+
+// ---- locator scan ----
+int zpaqgpu_find_blocks(zpaqgpu_ctx *ctx, const uint8_t *arc, uint64_t len, uint64_t *starts, int cap,
+                        int *n_found) {
+    if (!ctx || (len && !arc) || cap < 0 || !n_found) return ZPAQGPU_E_ARG;
+    *n_found = 0;
+    if (len == 0) return ZPAQGPU_OK;
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    int rc;
+    if ((rc = ensure(ctx, ctx->in, len))) return rc;
+    const u32 dcap = u32(std::max(cap, 1024));
+    if ((rc = ensure(ctx, ctx->results, 8 * size_t(dcap)))) return rc;
+    if ((rc = ensure(ctx, ctx->misc, 64))) return rc;
+    CK(cudaMemcpyAsync(ctx->in.p, arc, len, cudaMemcpyHostToDevice, st));
+    CK(cudaMemsetAsync(ctx->misc.p, 0, 64, st));
+    launch_find_blocks(static_cast<const u8 *>(ctx->in.p), len, static_cast<u64 *>(ctx->results.p), dcap,
+                       static_cast<u32 *>(ctx->misc.p), st);
+    CK(cudaGetLastError());
+    u32 count = 0;
+    CK(cudaMemcpyAsync(&count, ctx->misc.p, 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    *n_found = int(count);
+    if (count > u32(cap)) return ZPAQGPU_E_NOSPACE;
+    std::vector<u64> tmp(count);
+    if (count) CK(cudaMemcpy(tmp.data(), ctx->results.p, 8 * size_t(count), cudaMemcpyDeviceToHost));
+    std::sort(tmp.begin(), tmp.end());
+    if (count) std::memcpy(starts, tmp.data(), 8 * size_t(count));
+    return ZPAQGPU_OK;
+}
+
+// ---- whole-archive decompression ----
+int zpaqgpu_decompress_archive(zpaqgpu_ctx *ctx, const uint8_t *arc, uint64_t len, uint8_t *out, uint64_t out_cap,
+                               uint64_t *out_need, zpaqgpu_segment *segs, int segs_cap, int *n_segs) {
+    if (!ctx || (len && !arc)) return ZPAQGPU_E_ARG;
+    if (out_need) *out_need = 0;
+    if (n_segs) *n_segs = 0;
+    if (len == 0) return ZPAQGPU_OK;
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    int rc;
+    // 1. archive to the device, locator scan
+    if ((rc = ensure(ctx, ctx->in, len))) return rc;
+    CK(cudaEventRecord(ctx->ev[6], st));
+    CK(cudaMemcpyAsync(ctx->in.p, arc, len, cudaMemcpyHostToDevice, st));
+    CK(cudaEventRecord(ctx->ev[7], st));
+    u32 dcap = 1u << 16;
+    std::vector<u64> starts;
+    for (;;) {
+        if ((rc = ensure(ctx, ctx->results, 8 * size_t(dcap)))) return rc;
+        if ((rc = ensure(ctx, ctx->misc, 64))) return rc;
+        CK(cudaMemsetAsync(ctx->misc.p, 0, 64, st));
+        launch_find_blocks(static_cast<const u8 *>(ctx->in.p), len, static_cast<u64 *>(ctx->results.p), dcap,
+                           static_cast<u32 *>(ctx->misc.p), st);
+        CK(cudaGetLastError());
+        u32 count = 0;
+        CK(cudaMemcpyAsync(&count, ctx->misc.p, 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        if (count > dcap) { dcap = count + 1024; continue; }
+        starts.resize(count);
+        if (count) CK(cudaMemcpy(starts.data(), ctx->results.p, 8 * size_t(count), cudaMemcpyDeviceToHost));
+        break;
+    }
+    const float h2d_ms = elapsed(ctx->ev[6], ctx->ev[7]);
+    std::sort(starts.begin(), starts.end());
+    // 2. headers (decompressor.v:257-342).  Every candidate is decoded optimistically; candidates
+    //    that turn out to lie inside an earlier block are dropped in step 4.
+    DecompressJob job;
+    job.d_arc = static_cast<const u8 *>(ctx->in.p), job.arc_len = len;
+    std::map<std::vector<uint8_t>, int> group_of;
+    for (u64 s : starts) {
+        DecCandidate c;
+        c.start = s;
+        Model m;
+        u64 used = 0;
+        const int hrc = model_from_archive(arc + s, len - s, m, &used);
+        c.payload = s + used;
+        if (hrc == ZPAQGPU_OK) {
+            auto it = group_of.find(m.header);
+            if (it == group_of.end()) {
+                it = group_of.emplace(m.header, int(job.models.size())).first;
+                job.models.push_back(m);
+            }
+            c.group = it->second;
+            const u64 hint = comment_hint(arc, len, c.payload);
+            c.hint = hint ? hint : 4 * (len - c.payload > (1u << 20) ? (1u << 20) : len - c.payload) + 65536;
+        } else {
+            c.group = hrc == ZPAQGPU_E_UNSUPPORTED ? -2 : -1;
+            c.hint = 0;
+        }
+        job.cand.push_back(c);
+    }
+    // 3. decode
+    if (!job.cand.empty() && !job.models.empty()) {
+        // rejected headers get a dummy group so indices stay aligned; they are never launched
+        if ((rc = run_decompress(ctx, job, false))) return rc;
+    }
+    ctx->stats.h2d_ms = h2d_ms;
+    ctx->stats.pack_ms = 0;
+    // 4. walk the candidates the way repeated find_block calls would (decompressor.v:219-346)
+    u64 pos = 0, total = 0;
+    int seg_total = 0, block_index = 0;
+    int status = ZPAQGPU_OK;
+    struct Piece { u64 src, len; };
+    std::vector<Piece> pieces;
+    size_t rec_at = 0;
+    for (size_t i = 0; i < job.cand.size(); ++i) {
+        const DecCandidate &c = job.cand[i];
+        // a later find_block call restarts its rolling hashes at `pos`, so it only sees locators
+        // that lie completely behind the previous block; anything earlier is inside that block
+        if (pos > 0 && c.start < pos + 16) continue;
+        if (c.group < 0) {
+            // find_block returns false here and `for find_block {}` ends (cmd/main.v:349)
+            status = c.group == -2 ? ZPAQGPU_E_UNSUPPORTED : ZPAQGPU_OK;
+            break;
+        }
+        while (rec_at < job.recs.size() && job.recs[rec_at].block < u32(i)) ++rec_at;
+        size_t r = rec_at;
+        for (; r < job.recs.size() && job.recs[r].block == u32(i); ++r) {
+            const DecSegRec &rec = job.recs[r];
+            if (segs && seg_total < segs_cap) {
+                zpaqgpu_segment &o = segs[seg_total];
+                o.block_start = c.start, o.block_end = c.res.end_pos;
+                o.name_off = rec.name_off, o.comment_off = rec.comment_off;
+                o.out_off = total, o.out_len = rec.out_len;
+                o.block_index = block_index, o.sha1_ok = job.sha_ok[r];
+            }
+            pieces.push_back(Piece{rec.out_off, rec.out_len});
+            total += rec.out_len;
+            ++seg_total;
+        }
+        if (c.res.status != ZPAQGPU_OK && status == ZPAQGPU_OK) status = c.res.status;
+        pos = c.res.end_pos;
+        ++block_index;
+        if (c.res.status != ZPAQGPU_OK) break;
+    }
+    if (out_need) *out_need = total;
+    if (n_segs) *n_segs = seg_total;
+    if (total > out_cap || (segs && seg_total > segs_cap)) return ZPAQGPU_E_NOSPACE;
+    if (total && !out) return ZPAQGPU_E_ARG;
+    // 5. plaintext back to the host: contiguous runs of the arena are merged into single copies
+    CK(cudaEventRecord(ctx->ev[6], st));
+    u64 dst = 0;
+    for (size_t k = 0; k < pieces.size();) {
+        u64 src = pieces[k].src, run = pieces[k].len;
+        size_t j = k + 1;
+        while (j < pieces.size() && pieces[j].src == src + run) run += pieces[j].len, ++j;
+        if (run) CK(cudaMemcpyAsync(out + dst, job.d_plain + src, run, cudaMemcpyDeviceToHost, st));
+        dst += run;
+        k = j;
+    }
+    CK(cudaEventRecord(ctx->ev[7], st));
+    CK(cudaStreamSynchronize(st));
+    ctx->stats.d2h_ms = elapsed(ctx->ev[6], ctx->ev[7]);
+    return status;
+}
+
+int zpaqgpu_decompress_blocks_dev(zpaqgpu_ctx *ctx, const void *d_arc, const uint64_t *h_arc_off, int n_blocks,
+                                  void *d_out, const uint64_t *h_out_off, void *d_out_len, int *n_bad) {
+    if (!ctx || n_blocks <= 0 || !d_arc || !h_arc_off || !d_out || !h_out_off) return ZPAQGPU_E_ARG;
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    int rc;
+    // block heads to the host for header parsing
+    const u32 head = 512;
+    if ((rc = ensure(ctx, ctx->heads, size_t(head) * size_t(n_blocks) + 8 * size_t(n_blocks + 1)))) return rc;
+    u64 *d_off = reinterpret_cast<u64 *>(static_cast<u8 *>(ctx->heads.p) + size_t(head) * size_t(n_blocks));
+    d_off = reinterpret_cast<u64 *>(align_up(reinterpret_cast<uintptr_t>(d_off), 8));
+    if ((rc = ensure(ctx, ctx->out_off, 8 * size_t(n_blocks + 1)))) return rc;
+    CK(cudaMemcpyAsync(ctx->out_off.p, h_arc_off, 8 * size_t(n_blocks + 1), cudaMemcpyHostToDevice, st));
+    launch_gather_heads(static_cast<const u8 *>(d_arc), static_cast<const u64 *>(ctx->out_off.p), n_blocks, head,
+                        static_cast<u8 *>(ctx->heads.p), st);
+    CK(cudaGetLastError());
+    std::vector<uint8_t> heads(size_t(head) * size_t(n_blocks));
+    CK(cudaMemcpyAsync(heads.data(), ctx->heads.p, heads.size(), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    DecompressJob job;
+    job.d_arc = static_cast<const u8 *>(d_arc), job.arc_len = h_arc_off[n_blocks];
+    job.d_plain = static_cast<u8 *>(d_out);
+    std::map<std::vector<uint8_t>, int> group_of;
+    for (int b = 0; b < n_blocks; ++b) {
+        const uint8_t *hp = heads.data() + size_t(head) * size_t(b);
+        const u64 avail = std::min<u64>(head, h_arc_off[b + 1] - h_arc_off[b]);
+        DecCandidate c;
+        if (avail < 16) return ctx->err = "block shorter than its locator", ZPAQGPU_E_FORMAT;
+        c.start = h_arc_off[b] + 16;
+        Model m;
+        u64 used = 0;
+        const int hrc = model_from_archive(hp + 16, avail - 16, m, &used);
+        if (hrc != ZPAQGPU_OK) return ctx->err = "block " + std::to_string(b) + ": " + m.error, hrc;
+        c.payload = c.start + used;
+        auto it = group_of.find(m.header);
+        if (it == group_of.end()) {
+            it = group_of.emplace(m.header, int(job.models.size())).first;
+            job.models.push_back(m);
+        }
+        c.group = it->second;
+        c.out_off = h_out_off[b];
+        c.hint = h_out_off[b + 1] - h_out_off[b];
+        job.cand.push_back(c);
+    }
+    if ((rc = run_decompress(ctx, job, true))) return rc;
+    int bad = 0;
+    std::vector<u64> lens(static_cast<size_t>(n_blocks));
+    for (int b = 0; b < n_blocks; ++b) {
+        lens[size_t(b)] = job.cand[size_t(b)].res.out_len;
+        if (job.cand[size_t(b)].res.status != ZPAQGPU_OK) ++bad;
+    }
+    for (size_t r = 0; r < job.recs.size(); ++r)
+        if (job.sha_ok[r] == 0) ++bad;
+    if (d_out_len) CK(cudaMemcpy(d_out_len, lens.data(), 8 * size_t(n_blocks), cudaMemcpyHostToDevice));
+    if (n_bad) *n_bad = bad;
+    return ZPAQGPU_OK;
+}
+
+// ---- streaming-shaped calls ----
+int zpaqgpu_block_begin_header(zpaqgpu_ctx *ctx, const uint8_t *header, int header_len) {
+    if (!ctx) return ZPAQGPU_E_ARG;
+    if (ctx->st_state != 2) return ZPAQGPU_E_STATE;  // compressor.v:80-82
+    const int rc = model_from_level_layout(header, header_len, ctx->st_model);
+    if (rc) return ctx->err = ctx->st_model.error, rc;
+    ctx->st_segs.clear();
+    ctx->st_has_done = false;
+    ctx->st_state = 0;
+    return ZPAQGPU_OK;
+}
+int zpaqgpu_block_begin(zpaqgpu_ctx *ctx, int level) {
+    const std::vector<uint8_t> h = level_header(level);
+    return zpaqgpu_block_begin_header(ctx, h.data(), int(h.size()));
+}
+int zpaqgpu_segment_begin(zpaqgpu_ctx *ctx, const char *filename, const char *comment) {
+    if (!ctx) return ZPAQGPU_E_ARG;
+    if (ctx->st_state != 0) return ZPAQGPU_E_STATE;  // compressor.v:213-215
+    PendingSeg s;
+    s.name = filename ? filename : "", s.comment = comment ? comment : "";
+    ctx->st_segs.push_back(std::move(s));
+    ctx->st_state = 1;
+    return ZPAQGPU_OK;
+}
+int zpaqgpu_segment_write(zpaqgpu_ctx *ctx, const uint8_t *data, uint64_t len) {
+    if (!ctx || (len && !data)) return ZPAQGPU_E_ARG;
+    if (ctx->st_state != 1) return ZPAQGPU_E_STATE;  // compressor.v:260-262
+    PendingSeg &s = ctx->st_segs.back();
+    s.called = true;
+    s.data.insert(s.data.end(), data, data + len);
+    return ZPAQGPU_OK;
+}
+int zpaqgpu_segment_end(zpaqgpu_ctx *ctx) {
+    if (!ctx) return ZPAQGPU_E_ARG;
+    if (ctx->st_state != 1) return ZPAQGPU_E_STATE;  // compressor.v:358-360
+    ctx->st_state = 0;
+    return ZPAQGPU_OK;
+}
+int64_t zpaqgpu_block_end(zpaqgpu_ctx *ctx, uint8_t *out, uint64_t cap, uint64_t *need) {
+    if (!ctx) return ZPAQGPU_E_ARG;
+    if (!ctx->st_has_done) {
+        if (ctx->st_state != 0) return ZPAQGPU_E_STATE;  // compressor.v:403-405
+        if (cudaSetDevice(ctx->device) != cudaSuccess) return ZPAQGPU_E_NODEVICE;
+        const Model &m = ctx->st_model;
+        const int n_segs = int(ctx->st_segs.size());
+        std::vector<uint8_t> &done = ctx->st_done;
+        done.clear();
+        if (n_segs == 0) {
+            // a block without segments is just its header and 0xFF (compressor.v:150-181, :409)
+            done = m.block_prefix;
+            done.push_back(0xFF);
+        } else {
+            u64 total_in = 0;
+            for (const PendingSeg &s : ctx->st_segs) total_in += s.data.size();
+            std::vector<uint8_t> flat;
+            flat.reserve(size_t(total_in));
+            CompressJob job;
+            job.model = &m;
+            job.blocks.push_back(EncBlock{0, u32(n_segs)});
+            u64 worst = m.block_prefix.size() + 64;
+            for (const PendingSeg &s : ctx->st_segs) {
+                SegSpec sp;
+                sp.name = s.name.c_str(), sp.comment = s.comment.c_str();
+                sp.in_off = flat.size(), sp.in_len = s.data.size(), sp.called = s.called;
+                flat.insert(flat.end(), s.data.begin(), s.data.end());
+                job.segs.push_back(sp);
+                worst += sp.in_len + sp.in_len / 4 + 2048 + s.name.size() + s.comment.size();
+            }
+            int rc;
+            if ((rc = ensure(ctx, ctx->in, std::max<u64>(total_in, 16)))) return rc;
+            if (total_in &&
+                cudaMemcpyAsync(ctx->in.p, flat.data(), total_in, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess)
+                return ZPAQGPU_E_CUDA;
+            if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) return ZPAQGPU_E_CUDA;
+            for (int attempt = 0; attempt < 2; ++attempt) {
+                if ((rc = ensure(ctx, ctx->out, worst))) return rc;
+                if ((rc = ensure(ctx, ctx->out_off, 16))) return rc;
+                job.d_in = static_cast<const u8 *>(ctx->in.p);
+                job.d_out = static_cast<u8 *>(ctx->out.p), job.out_cap = ctx->out.cap;
+                job.d_out_off = static_cast<u64 *>(ctx->out_off.p);
+                if ((rc = run_compress(ctx, job))) return rc;
+                if (job.fits) break;
+                worst = job.total;
+            }
+            if (!job.fits) return ZPAQGPU_E_NOSPACE;
+            done.resize(size_t(job.total));
+            if (job.total && cudaMemcpy(done.data(), ctx->out.p, job.total, cudaMemcpyDeviceToHost) != cudaSuccess)
+                return ZPAQGPU_E_CUDA;
+        }
+        ctx->st_has_done = true;
+    }
+    if (need) *need = ctx->st_done.size();
+    if (ctx->st_done.size() > cap || (!out && !ctx->st_done.empty())) return ZPAQGPU_E_NOSPACE;
+    if (!ctx->st_done.empty()) std::memcpy(out, ctx->st_done.data(), ctx->st_done.size());
+    const int64_t n = int64_t(ctx->st_done.size());
+    ctx->st_has_done = false;
+    ctx->st_done.clear();
+    ctx->st_segs.clear();
+    ctx->st_state = 2;
+    return n;
+}
+
+}  // extern "C"
