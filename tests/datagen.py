@@ -42,35 +42,71 @@ def _vocabulary(seed):
 _vocab_cache = {}
 
 
-def text(n, seed=SEED0):
-    """n bytes of word-sampled text: Zipf(s=1.1) over a 4096-word vocabulary, newline every ~72 chars."""
-    if n == 0:
-        return b""
-    if "v" not in _vocab_cache:  # one fixed vocabulary for every seed
-        _vocab_cache["v"] = _vocabulary(SEED0)
-    words = _vocab_cache["v"]
-    ranks = np.arange(1, 4097, dtype=np.float64)
-    w = ranks ** -1.1
-    cdf = np.cumsum(w) / w.sum()
-    n_words = n // 4 + 16
+def _vocab_arrays():
+    """The fixed vocabulary as a padded byte matrix (word + separator slot) and word lengths."""
+    if "v" not in _vocab_cache:
+        words = _vocabulary(SEED0)
+        mat = np.zeros((4096, 13), dtype=np.uint8)
+        lens = np.zeros(4096, dtype=np.int64)
+        for i, w in enumerate(words):
+            mat[i, :len(w)] = np.frombuffer(w, dtype=np.uint8)
+            lens[i] = len(w)
+        ranks = np.arange(1, 4097, dtype=np.float64)
+        wgt = ranks ** -1.1
+        _vocab_cache["v"] = (mat, lens, np.cumsum(wgt) / wgt.sum())
+    return _vocab_cache["v"]
+
+
+def _text_chunk(n, seed):
+    mat, lens, cdf = _vocab_arrays()
+    n_words = n // 3 + 64  # mean word length with separator is well above 3
     u = (_xorshift_stream(seed, n_words) >> np.uint64(11)).astype(np.float64) / float(1 << 53)
     idx = np.searchsorted(cdf, u)
-    out = bytearray()
-    col = 0
-    for i in idx:
-        wd = words[int(i)]
-        out += wd
-        col += len(wd) + 1
-        if col >= 72:
-            out += b"\n"
-            col = 0
-        else:
-            out += b" "
-        if len(out) >= n:
-            break
-    while len(out) < n:
-        out += b" "
-    return bytes(out[:n])
+    wl = lens[idx] + 1                       # word + separator
+    end = np.cumsum(wl)
+    start = end - wl
+    keep = int(np.searchsorted(end, n, side="left")) + 1
+    idx, wl, end, start = idx[:keep], wl[:keep], end[:keep], start[:keep]
+    out = np.full(int(end[-1]), 32, dtype=np.uint8)
+    for j in range(12):
+        sel = wl - 1 > j
+        out[start[sel] + j] = mat[idx[sel], j]
+    # the separator becomes a newline where the running column crosses a multiple of 72
+    line = end // 72
+    brk = np.empty(keep, dtype=bool)
+    brk[0] = line[0] > 0
+    brk[1:] = line[1:] > line[:-1]
+    out[end[brk] - 1] = 10
+    return out[:n]
+
+
+CHUNK = 8 << 20  # text is generated in independent 8 MiB chunks so that ranges can be produced alone
+
+
+def text_range(first, n, seed=SEED0, threads=None):
+    """Bytes [first, first+n) of the endless text stream of `seed` (chunk-parallel)."""
+    if n == 0:
+        return b""
+    from concurrent.futures import ThreadPoolExecutor
+    import os
+    c0, c1 = first // CHUNK, (first + n - 1) // CHUNK
+    _vocab_arrays()
+    ids = list(range(c0, c1 + 1))
+    workers = threads or min(len(ids), os.cpu_count() or 1)
+    if workers > 1:
+        with ThreadPoolExecutor(workers) as ex:
+            parts = list(ex.map(lambda k: _text_chunk(CHUNK, seed + 0x9E37 * k), ids))
+    else:
+        parts = [_text_chunk(CHUNK, seed + 0x9E37 * k) for k in ids]
+    whole = np.concatenate(parts) if len(parts) > 1 else parts[0]
+    lo = first - c0 * CHUNK
+    return whole[lo:lo + n].tobytes()
+
+
+def text(n, seed=SEED0):
+    """n bytes of word-sampled text: Zipf(s=1.1) over a fixed 4096-word lowercase vocabulary
+    (word length 2..12, English letter frequencies), separated by spaces, newline every ~72 chars."""
+    return text_range(0, n, seed)
 
 
 def random_bytes(n, seed=SEED0 + 1):
@@ -111,3 +147,8 @@ def text_blocks(n_blocks, block_bytes, seed=SEED0):
     """A long text stream cut into blocks (cfg 2); generated once and sliced."""
     whole = text(n_blocks * block_bytes, seed)
     return [whole[i * block_bytes:(i + 1) * block_bytes] for i in range(n_blocks)]
+
+
+def text_stream(n, seed=SEED0, first=0):
+    """numpy uint8 view of text_range, for bench.py (no per-block slicing copies)."""
+    return np.frombuffer(text_range(first, n, seed), dtype=np.uint8)
