@@ -2,20 +2,24 @@
 // level has (levels.v:53-375):  ICM -> ISSE -> ... -> ISSE [-> MIX2 of the last two ISSEs], with
 // the context hashes coming from one of the two HCOMP programs the levels use.
 //
-// Mapping (sm_100a):
-//  * one ZPAQ block per warp; W warps (blocks) per CTA, one CTA per SM;
-//  * squash/stretch/next-state tables (72.5 KiB) live in shared memory, shared by the CTA;
-//  * each block's adaptive tables (ICM cm[256], ISSE weight pairs[256] per ISSE: 1 + 2*NI KiB)
-//    live in shared memory, private to the warp;
-//  * the big hash tables stay in HBM/L2.  A probe (Predictor.find_ht, predictor.v:495-532)
-//    touches one 64-byte line; lane i probes for component i with three 16-byte vector loads, the
-//    winning 16-byte slot is parked in shared memory for the four bits of the nibble and written
-//    back with one 16-byte store at the next nibble boundary;
-//  * the bit-serial chain (predict -> code -> update) runs on lane 0 out of registers and shared
-//    memory; the coder's low/high/code stay in registers; plaintext/code bytes are staged through
-//    shared-memory rings and moved to/from HBM by the whole warp;
-//  * MIX2 weights for the 256 possible c8 values of the current byte are staged in shared memory
-//    at each byte boundary.
+// Mapping (sm_100a): one ZPAQ block per warp, ONE MODEL COMPONENT PER LANE.
+//  * lane 0 owns the ICM, lanes 1..NI the ISSEs.  Each lane keeps the 16-byte hash slot of its
+//    component for the current nibble in four registers, extracts the bit-history state of the
+//    current tree node with a shift, and reads its adaptive table entry (ICM {cm, stretch(cm>>8)},
+//    ISSE {wt0, wt1}) from shared memory with one 64-bit load;
+//  * the ISSE chain p[i] = clamp2k((wt0*p[i-1] + wt1*64) >> 16) is a serial dependency across
+//    components: the 2*NI weights are all-gathered with warp shuffles and every lane evaluates the
+//    chain redundantly in registers, so no lane waits on a neighbour's arithmetic;
+//  * the arithmetic coder (low/high/code) is evaluated redundantly by all lanes out of registers:
+//    the decoded bit is known warp-wide without a broadcast; code/plaintext bytes are staged
+//    through shared-memory rings and moved to/from HBM by the whole warp;
+//  * each lane updates its own table entry and inserts the successor state into its slot
+//    registers; at a nibble boundary each lane writes its slot back to HBM with one 16-byte store
+//    and probes the next one (Predictor.find_ht, predictor.v:495-532: three 16-byte loads inside
+//    one 64-byte line);
+//  * squash/stretch/next-state tables (72.5 KiB) are shared by the CTA in shared memory, each
+//    block's adaptive tables (2 KiB per component) are private to its warp; MIX2 weights for the
+//    256 possible c8 values of the current byte are staged in shared memory per byte.
 #include "../../include/zpaqgpu.h"
 #include "common.cuh"
 #include "kernels.h"
@@ -29,67 +33,79 @@ constexpr u32 kNoSlot = 0xFFFFFFFFu;
 constexpr unsigned kFull = 0xFFFFFFFFu;
 
 __host__ __device__ constexpr size_t warp_smem_bytes(int ni, bool mix2) {
-    return size_t(256) * 4                 // ICM cm
-           + size_t(ni) * 256 * 8          // ISSE weight pairs
-           + size_t(ni + 1) * 16           // parked hash slots
+    return size_t(ni + 1) * 256 * 8        // ICM {cm, stretch} pairs, then ISSE weight pairs
+           + 256                           // store sink for lanes that own no component
            + (mix2 ? 512 : 0)              // staged MIX2 weights
            + kRing + kOutStage;
 }
 constexpr size_t kSharedTables = 32768 * 2 + 4096 * 2 + 512;
+
+__device__ __forceinline__ uint4 ldg128(const u8 *p) {
+    uint4 v;
+    asm volatile("ld.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
+}
 
 template <int NI, bool MIX2>
 struct Chain {
     // shared-memory views
     const int16_t *stretch;
     const u16 *squash;
-    const u8 *nex;
-    u32 *cm0;
-    int2 *wt;
-    u8 *slots;   // (NI+1) x 16 bytes
+    const u16 *nex16;  // nex16[s] = next(s,0) | next(s,1) << 8
+    int2 *tab;         // this lane's table: ICM {cm[s], stretch(cm[s]>>8)} or ISSE {wt0, wt1}
+    int2 *dump;        // 32 entries nobody reads
     u16 *a16s;
     u8 *ring;
     u8 *stage;
-    // per-lane: the hash table of component `lane`
+    // per lane: the hash table of component `lane`, its parked slot and context hash
     u8 *ht;
     u32 ht_len;
     int sizebits;
     u32 slot_at;
-    u32 h;        // context hash of component `lane` for the current byte
+    uint4 sl;
+    u32 h;
+    bool owner;        // lane <= NI
     // MIX2
     u16 *a16;
     u32 a16_mask, mix_h, mix_sel;
     i32 mix_rate;
     // context history (uniform)
     int ctx_mode, n_hash, n_comp;
-    u32 hist;     // CTX_M1: previous three bytes (b1 | b2<<8 | b3<<16); CTX_HASHCHAIN: previous byte
+    u32 hist;          // CTX_M1: previous three bytes; CTX_HASHCHAIN: previous byte
     int lane;
 
     __device__ void setup(u8 *smem_warp, const ModelDev &M, u8 *ws, const int16_t *st, const u16 *sq,
                           const u8 *nx) {
         lane = threadIdx.x & 31;
-        stretch = st, squash = sq, nex = nx;
+        owner = lane <= NI;
+        stretch = st, squash = sq, nex16 = reinterpret_cast<const u16 *>(nx);
         u8 *p = smem_warp;
-        cm0 = reinterpret_cast<u32 *>(p), p += 1024;
-        wt = reinterpret_cast<int2 *>(p), p += size_t(NI) * 2048;
-        slots = p, p += (NI + 1) * 16;
+        int2 *tables = reinterpret_cast<int2 *>(p);
+        p += size_t(NI + 1) * 2048;
+        dump = reinterpret_cast<int2 *>(p), p += 256;
         a16s = reinterpret_cast<u16 *>(p), p += MIX2 ? 512 : 0;
         ring = p, p += kRing;
         stage = p;
+        tab = tables + (owner ? lane : 0) * 256;
         ctx_mode = M.ctx_mode, n_hash = M.n_hash, n_comp = M.n;
         // adaptive tables: the fill kernel wrote their initial images into the workspace
         const u32 *src0 = reinterpret_cast<const u32 *>(ws + M.comps[0].cm_off);
-        for (int k = lane; k < 256; k += 32) cm0[k] = src0[k];
+        for (int k = lane; k < 256; k += 32) {
+            const u32 v = src0[k];
+            tables[k] = make_int2(i32(v), i32(st[d_stretch_idx(i32(v >> 8))]));
+        }
 #pragma unroll
-        for (int i = 0; i < NI; ++i) {
-            const int2 *src = reinterpret_cast<const int2 *>(ws + M.comps[i + 1].cm_off);
-            for (int k = lane; k < 256; k += 32) wt[i * 256 + k] = src[k];
+        for (int i = 1; i <= NI; ++i) {
+            const int2 *src = reinterpret_cast<const int2 *>(ws + M.comps[i].cm_off);
+            for (int k = lane; k < 256; k += 32) tables[i * 256 + k] = src[k];
         }
         ht = nullptr, ht_len = 16, sizebits = 0;
-        if (lane <= NI) {
+        if (owner) {
             const CompDesc &cd = M.comps[lane];
             ht = ws + cd.ht_off, ht_len = cd.ht_len, sizebits = cd.a + 2;
         }
         slot_at = kNoSlot;
+        sl = make_uint4(0, 0, 0, 0);
         h = 0, hist = 0, mix_h = 0;
         a16 = nullptr, a16_mask = 0, mix_sel = 0, mix_rate = 0;
         if (MIX2) {
@@ -143,77 +159,86 @@ struct Chain {
         }
     }
 
-    // Predictor.find_ht for component `lane` (predictor.v:495-532), whole warp converged.
-    __device__ void probe(u32 c8v) {
-        __syncwarp();
-        if (lane <= NI) {
-            uint4 *park = reinterpret_cast<uint4 *>(slots) + lane;
-            if (slot_at != kNoSlot) *reinterpret_cast<uint4 *>(ht + slot_at) = *park;
+    // Predictor.find_ht for component `lane` (predictor.v:495-532).  The slot of the previous
+    // nibble goes back to its table first (the reference updates the table in place).
+    __device__ __forceinline__ void probe(u32 c8v) {
+        if (owner) {
+            if (slot_at != kNoSlot) *reinterpret_cast<uint4 *>(ht + slot_at) = sl;
             const u32 key = h + 16u * c8v;
             const u32 chk = (key >> sizebits) & 255u;
             const u32 h0 = (key * 16u) & (ht_len - 16u), h1 = h0 ^ 16u, h2 = h0 ^ 32u;
-            const uint4 s0 = *reinterpret_cast<const uint4 *>(ht + h0);
-            const uint4 s1 = *reinterpret_cast<const uint4 *>(ht + h1);
-            const uint4 s2 = *reinterpret_cast<const uint4 *>(ht + h2);
-            uint4 pick;
-            u32 at;
-            if ((s0.x & 255u) == chk) {
-                pick = s0, at = h0;
-            } else if ((s1.x & 255u) == chk) {
-                pick = s1, at = h1;
-            } else if ((s2.x & 255u) == chk) {
-                pick = s2, at = h2;
-            } else {
-                const u32 q0 = (s0.x >> 8) & 255u, q1 = (s1.x >> 8) & 255u, q2 = (s2.x >> 8) & 255u;
-                at = (q0 <= q1 && q0 <= q2) ? h0 : (q1 < q2 ? h1 : h2);
-                pick = make_uint4(chk, 0u, 0u, 0u);
-            }
-            *park = pick;
-            slot_at = at;
+            // All three candidates are requested before any is looked at and the choice is made
+            // with selects: written as an if-chain the compiler makes the second and third load
+            // conditional, which serialises three HBM round trips.
+            const uint4 s0 = ldg128(ht + h0), s1 = ldg128(ht + h1), s2 = ldg128(ht + h2);
+            const bool m0 = (s0.x & 255u) == chk, m1 = (s1.x & 255u) == chk, m2 = (s2.x & 255u) == chk;
+            const u32 q0 = (s0.x >> 8) & 255u, q1 = (s1.x >> 8) & 255u, q2 = (s2.x >> 8) & 255u;
+            const u32 victim = (q0 <= q1 && q0 <= q2) ? h0 : (q1 < q2 ? h1 : h2);
+            const bool hit = m0 | m1 | m2;
+            slot_at = m0 ? h0 : m1 ? h1 : m2 ? h2 : victim;
+            uint4 pick = m0 ? s0 : (m1 ? s1 : s2);
+            sl.x = hit ? pick.x : chk;
+            sl.y = hit ? pick.y : 0u;
+            sl.z = hit ? pick.z : 0u;
+            sl.w = hit ? pick.w : 0u;
         }
-        __syncwarp();
     }
 };
 
-// Four coded bits of one nibble on lane 0.  ENC: `nib` holds the 4 bits, MSB first.
-// Returns the nibble (decoder) / nib (encoder).  c8 enters as 1 (high nibble) or 16..31.
+// Four coded bits of one nibble, whole warp converged (predictor.v:536-824 for the ICM/ISSE/MIX2
+// chain, encoder.v:48-89 / decoder.v:73-118).  ENC: `nib` holds the 4 bits, MSB first; DEC: returns
+// them.  c8 enters as 1 (high nibble) or 16..31 (low nibble).
 template <int NI, bool MIX2, bool DEC, class IO>
 __device__ __forceinline__ u32 code_nibble(Chain<NI, MIX2> &C, u32 nib, u32 &c8, u32 &low, u32 &high,
                                            u32 &code, IO &io) {
+    const int lane = C.lane;
     u32 idx = 1;
     u32 got = 0;
-#pragma unroll 1
-    for (int k = 3; k >= 0; --k) {
-        // ---- predict (predictor.v:555-563, :615-631, :586-599) ----
-        i32 p[NI + 2];
-        u32 st[NI + 1];
-        int2 w[NI + 1];
-        st[0] = C.slots[idx];
-        const u32 v0 = C.cm0[st[0]];
-        p[0] = C.stretch[d_stretch_idx(i32(v0 >> 8))];
 #pragma unroll
-        for (int i = 1; i <= NI; ++i) {
-            st[i] = C.slots[i * 16 + idx];
-            w[i] = C.wt[(i - 1) * 256 + st[i]];
-        }
-#pragma unroll
-        for (int i = 1; i <= NI; ++i) p[i] = d_clamp2k((w[i].x * p[i - 1] + w[i].y * 64) >> 16);
+    for (int k = 0; k < 4; ++k) {
+        // ---- bit-history state of tree node idx in this lane's slot (predictor.v:561, :622) ----
+        const u32 sh = (k == 0) ? 8u : (idx & 3u) * 8u;
+        const bool hiword = (k == 3) && (idx & 4u);
+        const u32 word = (k < 2) ? C.sl.x : (k == 2) ? C.sl.y : (hiword ? C.sl.w : C.sl.z);
+        const u32 st = (word >> sh) & 255u;
+        // ---- table reads of this bit ----
+        const int2 e = C.tab[st];
+        const u32 nx = C.nex16[st];
         i32 mw = 0;
         u32 msel = 0;
         if (MIX2) {
             msel = c8 & C.mix_sel;
             mw = C.a16s[msel];
-            p[NI + 1] = d_clamp2k((mw * p[NI - 1] + (65536 - mw) * p[NI]) >> 16);
         }
-        const i32 pl = MIX2 ? p[NI + 1] : p[NI];
-        const u32 p16 = u32(C.squash[d_squash_idx(pl)]) * 2u + 1u;
-        // ---- code (encoder.v:48-89 / decoder.v:73-118) ----
+        // ICM update candidates for y=0 / y=1 and their stretch values (predictor.v:706-708);
+        // meaningful on lane 0, harmless elsewhere
+        const u32 v0 = u32(e.x);
+        const i32 r0 = i32(v0 >> 8);
+        const u32 va = u32(i32(v0) + ((0 - r0) >> 2)), vb = u32(i32(v0) + ((32767 - r0) >> 2));
+        const i32 spa = C.stretch[d_stretch_idx(i32(va >> 8))], spb = C.stretch[d_stretch_idx(i32(vb >> 8))];
+        // ---- predict: all-gather the weights, evaluate the ISSE chain on every lane ----
+        i32 p = __shfl_sync(kFull, e.y, 0);  // p[0] = stretch(cm[state] >> 8)
+        i32 pin = 0, pout = p, pa = 0, pb = 0;
+#pragma unroll
+        for (int i = 1; i <= NI; ++i) {
+            const i32 w0 = __shfl_sync(kFull, e.x, i), w1 = __shfl_sync(kFull, e.y, i);
+            const i32 pn = d_clamp2k((w0 * p + w1 * 64) >> 16);
+            if (lane == i) pin = p, pout = pn;
+            if (MIX2 && i == NI - 1) pa = pn;
+            if (MIX2 && i == NI) pb = pn;
+            p = pn;
+        }
+        if (MIX2) p = d_clamp2k((mw * pa + (65536 - mw) * pb) >> 16);
+        const i32 sq_own = C.squash[d_squash_idx(pout)];
+        const i32 sq_fin = C.squash[d_squash_idx(p)];
+        const u32 p16 = u32(sq_fin) * 2u + 1u;
+        // ---- code ----
         const u32 mid = coder_mid(low, high, p16);
         u32 y;
         if (DEC) {
             y = code <= mid;
         } else {
-            y = (nib >> k) & 1u;
+            y = (nib >> (3 - k)) & 1u;
         }
         if (y) high = mid; else low = mid + 1;
         while ((high ^ low) < 0x1000000u) {
@@ -223,34 +248,42 @@ __device__ __forceinline__ u32 code_nibble(Chain<NI, MIX2> &C, u32 nib, u32 &c8,
             if (low == 0) low = 1;
             if (DEC) code = (code << 8) | io.get();
         }
-        // ---- update (predictor.v:701-709, :776-791, :744-762) ----
+        // ---- update this lane's component (predictor.v:701-709, :776-791) ----
         const i32 t = y ? 32767 : 0;
-        C.slots[idx] = C.nex[st[0] * 2 + y];
-        C.cm0[st[0]] = u32(i32(v0) + ((t - i32(v0 >> 8)) >> 2));
-#pragma unroll
-        for (int i = 1; i <= NI; ++i) {
-            const i32 err = t - i32(C.squash[d_squash_idx(p[i])]);
-            int2 nw;
-            nw.x = d_clamp512k(w[i].x + ((err * p[i - 1] + 4096) >> 13));
-            nw.y = d_clamp512k(w[i].y + ((err + 16) >> 5));
-            C.wt[(i - 1) * 256 + st[i]] = nw;
-            C.slots[i * 16 + idx] = C.nex[st[i] * 2 + y];
-        }
-        if (MIX2) {
-            const i32 err = ((t - i32(p16 >> 1)) * C.mix_rate) >> 5;
-            i32 nw = mw + ((err * (p[NI - 1] - p[NI]) + 4096) >> 13);
+        const i32 err = t - sq_own;
+        const i32 ix = d_clamp512k(e.x + ((err * pin + 4096) >> 13));
+        const i32 iy = d_clamp512k(e.y + ((err + 16) >> 5));
+        const i32 cx = i32(y ? vb : va), cy = y ? spb : spa;
+        const bool icm = lane == 0;
+        // non-owner lanes alias lane 0's table and write back what they read (st == 0 there is
+        // never lane 0's live state only if values match, so they must not store at all)
+        int2 *dstp = C.owner ? &C.tab[st] : &C.dump[lane];
+        *dstp = make_int2(icm ? cx : ix, icm ? cy : iy);
+        if (MIX2) {  // predictor.v:744-762, uniform values, one lane stores
+            const i32 merr = ((t - sq_fin) * C.mix_rate) >> 5;
+            i32 nw = mw + ((merr * (pa - pb) + 4096) >> 13);
             nw = max(0, min(65535, nw));
-            C.a16s[msel] = u16(nw);
-            C.a16[(C.mix_h + msel) & C.a16_mask] = u16(nw);
+            if (lane == NI + 1) {
+                C.a16s[msel] = u16(nw);
+                C.a16[(C.mix_h + msel) & C.a16_mask] = u16(nw);
+            }
         }
+        // successor state back into the slot registers (statetable.v:75-88)
+        const u32 ns = (nx >> (y * 8u)) & 255u;
+        const u32 d = (st ^ ns) << sh;
+        if (k < 2) C.sl.x ^= d;
+        else if (k == 2) C.sl.y ^= d;
+        else if (hiword) C.sl.w ^= d;
+        else C.sl.z ^= d;
         c8 = (c8 << 1) | y;
         idx = (idx * 2 + y) & 15u;
         got = (got << 1) | y;
+        if (MIX2) __syncwarp();  // the staged weight written by lane NI+1 may be re-read (mask < 255)
     }
     return got;
 }
 
-// ---- lane-0 byte I/O over the shared-memory stages ----
+// ---- byte I/O over the shared-memory stages (all lanes execute, same address) ----
 struct EncIO {
     u8 *stage;
     u32 fill;
@@ -264,7 +297,7 @@ struct DecIO {
     __device__ __forceinline__ u32 get() { return ring[(pos++) & (kRing - 1)]; }
 };
 
-// Keep at least `need` bytes of [pos, limit) in the ring; bytes past `limit` read as zero (the
+// Keep at least 64 bytes of [pos, limit) in the ring; bytes past `limit` read as zero (the
 // reference's get() returns -1 there and the decoder shifts in nothing, decoder.v:111-116).
 __device__ __forceinline__ void ring_fill(u8 *ring, const u8 *base, u64 pos, u64 &filled, u64 limit,
                                           int lane) {
@@ -280,6 +313,18 @@ __device__ __forceinline__ void ring_fill(u8 *ring, const u8 *base, u64 pos, u64
     }
 }
 
+__device__ __forceinline__ void load_shared_tables(u8 *smem, const DevTables &T) {
+    const uint4 *g = reinterpret_cast<const uint4 *>(T.stretch);
+    uint4 *d = reinterpret_cast<uint4 *>(smem);
+    for (int k = threadIdx.x; k < 4096; k += blockDim.x) d[k] = g[k];
+    const uint4 *g2 = reinterpret_cast<const uint4 *>(T.squash);
+    uint4 *d2 = reinterpret_cast<uint4 *>(smem + 65536);
+    for (int k = threadIdx.x; k < 512; k += blockDim.x) d2[k] = g2[k];
+    u8 *s_nex = smem + 65536 + 8192;
+    for (int k = threadIdx.x; k < 512; k += blockDim.x) s_nex[k] = T.nex[k];
+    __syncthreads();
+}
+
 }  // namespace
 
 // ------------------------------------------------------------------------------------------
@@ -288,26 +333,15 @@ __device__ __forceinline__ void ring_fill(u8 *ring, const u8 *base, u64 pos, u64
 template <int NI, bool MIX2>
 __global__ void __launch_bounds__(256, 1) k_encode_chain(EncodeArgs A) {
     extern __shared__ __align__(16) u8 smem[];
-    int16_t *s_stretch = reinterpret_cast<int16_t *>(smem);
-    u16 *s_squash = reinterpret_cast<u16 *>(smem + 65536);
-    u8 *s_nex = smem + 65536 + 8192;
-    {
-        const uint4 *g = reinterpret_cast<const uint4 *>(A.tables.stretch);
-        uint4 *d = reinterpret_cast<uint4 *>(s_stretch);
-        for (int k = threadIdx.x; k < 4096; k += blockDim.x) d[k] = g[k];
-        const uint4 *g2 = reinterpret_cast<const uint4 *>(A.tables.squash);
-        uint4 *d2 = reinterpret_cast<uint4 *>(s_squash);
-        for (int k = threadIdx.x; k < 512; k += blockDim.x) d2[k] = g2[k];
-        for (int k = threadIdx.x; k < 512; k += blockDim.x) s_nex[k] = A.tables.nex[k];
-    }
-    __syncthreads();
+    load_shared_tables(smem, A.tables);
     const int wic = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int slot = blockIdx.x * (blockDim.x >> 5) + wic;
     if (slot >= A.n_blocks) return;
     Chain<NI, MIX2> C;
     u8 *ws = A.workspace + u64(slot) * A.model.ws_bytes;
-    C.setup(smem + kSharedTables + size_t(wic) * warp_smem_bytes(NI, MIX2), A.model, ws, s_stretch,
-            s_squash, s_nex);
+    C.setup(smem + kSharedTables + size_t(wic) * warp_smem_bytes(NI, MIX2), A.model, ws,
+            reinterpret_cast<const int16_t *>(smem), reinterpret_cast<const u16 *>(smem + 65536),
+            smem + 65536 + 8192);
     const EncBlock blk = A.blocks[A.first_block + slot];
     for (u32 s = 0; s < blk.n_seg; ++s) {
         const EncSeg seg = A.segs[blk.first_seg + s];
@@ -327,59 +361,54 @@ __global__ void __launch_bounds__(256, 1) k_encode_chain(EncodeArgs A) {
                 ring_fill(C.ring, src, at, filled, seg.in_len, lane);
                 c = C.ring[at & (kRing - 1)];
             }
-            C.probe(1u);
-            u32 c8 = 1;
-            if (lane == 0) {
-                // "not EOF" flag: encode(0, p=0) => low += 1 (encoder.v:108)
-                low = low + 1;
-                while ((high ^ low) < 0x1000000u) {
-                    io.put(high >> 24);
-                    low <<= 8;
-                    high = (high << 8) | 0xFFu;
-                    if (low == 0) low = 1;
-                }
-                code_nibble<NI, MIX2, false>(C, c >> 4, c8, low, high, code, io);
-            }
-            C.probe(16u | (c >> 4));
-            if (lane == 0) {
-                c8 = 16u | (c >> 4);
-                code_nibble<NI, MIX2, false>(C, c & 15u, c8, low, high, code, io);
-            }
-            C.byte_end(c);
-            // move full 256-byte chunks of coded output to HBM
-            const u32 fill = __shfl_sync(kFull, io.fill, 0);
-            if (fill >= 256) {
-                __syncwarp();
-                u32 tail = 0;
-                if (lane + 256 < int(fill)) tail = C.stage[256 + lane];
-                for (int q = lane; q < 256; q += 32)
-                    if (written + q < seg.pay_cap) dst[written + q] = C.stage[q];
-                __syncwarp();
-                if (lane + 256 < int(fill)) C.stage[lane] = u8(tail);
-                // a byte can emit at most 36 coded bytes, so the tail beyond 256 fits 32 lanes + 4
-                for (int q = 288 + lane; q < int(fill); q += 32) C.stage[q - 256] = C.stage[q];
-                __syncwarp();
-                written += 256;
-                io.fill = fill - 256;
-            }
-        }
-        // EOF: encode(1, p=0) then flush the four bytes of high (encoder.v:101-105, :130-139)
-        if (lane == 0) {
-            high = low;
+            // "not EOF" flag: encode(0, p=0) => low += 1 (encoder.v:108)
+            low = low + 1;
             while ((high ^ low) < 0x1000000u) {
                 io.put(high >> 24);
                 low <<= 8;
                 high = (high << 8) | 0xFFu;
                 if (low == 0) low = 1;
             }
-            io.put(high >> 24), io.put((high >> 16) & 255u), io.put((high >> 8) & 255u), io.put(high & 255u);
+#pragma unroll 1
+            for (int half = 0; half < 2; ++half) {
+                u32 c8 = half ? (16u | (c >> 4)) : 1u;
+                C.probe(c8);
+                code_nibble<NI, MIX2, false>(C, half ? (c & 15u) : (c >> 4), c8, low, high, code, io);
+            }
+            C.byte_end(c);
+            // move full 256-byte chunks of coded output to HBM
+            if (io.fill >= 256) {
+                __syncwarp();
+                const u32 fill = io.fill;
+                u32 tail = 0;
+                if (lane + 256 < int(fill)) tail = C.stage[256 + lane];
+                for (int q = lane; q < 256; q += 32)
+                    if (written + q < seg.pay_cap) dst[written + q] = C.stage[q];
+                // a byte emits at most 36 coded bytes, so the tail beyond 256 is < 36 bytes
+                u32 tail2 = 0;
+                if (lane + 288 < int(fill)) tail2 = C.stage[288 + lane];
+                __syncwarp();
+                if (lane + 256 < int(fill)) C.stage[lane] = u8(tail);
+                if (lane + 288 < int(fill)) C.stage[32 + lane] = u8(tail2);
+                __syncwarp();
+                written += 256;
+                io.fill = fill - 256;
+            }
         }
-        const u32 fill = __shfl_sync(kFull, io.fill, 0);
+        // EOF: encode(1, p=0) then flush the four bytes of high (encoder.v:101-105, :130-139)
+        high = low;
+        while ((high ^ low) < 0x1000000u) {
+            io.put(high >> 24);
+            low <<= 8;
+            high = (high << 8) | 0xFFu;
+            if (low == 0) low = 1;
+        }
+        io.put(high >> 24), io.put((high >> 16) & 255u), io.put((high >> 8) & 255u), io.put(high & 255u);
         __syncwarp();
-        for (u32 q = lane; q < fill; q += 32)
+        for (u32 q = lane; q < io.fill; q += 32)
             if (written + q < seg.pay_cap) dst[written + q] = C.stage[q];
         __syncwarp();
-        if (lane == 0) A.pay_len[blk.first_seg + s] = written + fill;
+        if (lane == 0) A.pay_len[blk.first_seg + s] = written + io.fill;
     }
 }
 
@@ -389,27 +418,16 @@ __global__ void __launch_bounds__(256, 1) k_encode_chain(EncodeArgs A) {
 template <int NI, bool MIX2>
 __global__ void __launch_bounds__(256, 1) k_decode_chain(DecodeArgs A) {
     extern __shared__ __align__(16) u8 smem[];
-    int16_t *s_stretch = reinterpret_cast<int16_t *>(smem);
-    u16 *s_squash = reinterpret_cast<u16 *>(smem + 65536);
-    u8 *s_nex = smem + 65536 + 8192;
-    {
-        const uint4 *g = reinterpret_cast<const uint4 *>(A.tables.stretch);
-        uint4 *d = reinterpret_cast<uint4 *>(s_stretch);
-        for (int k = threadIdx.x; k < 4096; k += blockDim.x) d[k] = g[k];
-        const uint4 *g2 = reinterpret_cast<const uint4 *>(A.tables.squash);
-        uint4 *d2 = reinterpret_cast<uint4 *>(s_squash);
-        for (int k = threadIdx.x; k < 512; k += blockDim.x) d2[k] = g2[k];
-        for (int k = threadIdx.x; k < 512; k += blockDim.x) s_nex[k] = A.tables.nex[k];
-    }
-    __syncthreads();
+    load_shared_tables(smem, A.tables);
     const int wic = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int slot = blockIdx.x * (blockDim.x >> 5) + wic;
     if (slot >= A.n_blocks) return;
     const int bi = A.first_block + slot;
     Chain<NI, MIX2> C;
     u8 *ws = A.workspace + u64(slot) * A.model.ws_bytes;
-    C.setup(smem + kSharedTables + size_t(wic) * warp_smem_bytes(NI, MIX2), A.model, ws, s_stretch,
-            s_squash, s_nex);
+    C.setup(smem + kSharedTables + size_t(wic) * warp_smem_bytes(NI, MIX2), A.model, ws,
+            reinterpret_cast<const int16_t *>(smem), reinterpret_cast<const u16 *>(smem + 65536),
+            smem + 65536 + 8192);
     const DecBlock blk = A.blocks[bi];
     const u8 *arc = A.arc;
     u64 pos = blk.arc_pos;  // uniform across the warp
@@ -447,29 +465,25 @@ __global__ void __launch_bounds__(256, 1) k_decode_chain(DecodeArgs A) {
         bool unsupported = false;
         for (;;) {
             ring_fill(C.ring, arc, io.pos, filled, A.arc_len, lane);
-            u32 c8 = 1, eof = 0;
-            if (lane == 0) {
-                // EOF flag: decode(p=0) => y = (code <= low) (decoder.v:128-131)
-                eof = code <= low;
-                if (eof) high = low; else low = low + 1;
-                while ((high ^ low) < 0x1000000u) {
-                    low <<= 8;
-                    high = (high << 8) | 0xFFu;
-                    if (low == 0) low = 1;
-                    code = (code << 8) | io.get();
-                }
+            // EOF flag: decode(p=0) => y = (code <= low) (decoder.v:128-131)
+            const bool eof = code <= low;
+            if (eof) high = low; else low = low + 1;
+            while ((high ^ low) < 0x1000000u) {
+                low <<= 8;
+                high = (high << 8) | 0xFFu;
+                if (low == 0) low = 1;
+                code = (code << 8) | io.get();
             }
-            eof = __shfl_sync(kFull, eof, 0);
             if (eof) break;
             // the model is only consulted once a data byte is known to follow (decoder.v:128-142):
             // a probe at EOF could evict a slot that a later segment of the block still needs
-            C.probe(1u);
-            if (lane == 0) code_nibble<NI, MIX2, true>(C, 0, c8, low, high, code, io);
-            c8 = __shfl_sync(kFull, c8, 0);
-            C.probe(c8);
-            if (lane == 0) code_nibble<NI, MIX2, true>(C, 0, c8, low, high, code, io);
-            const u32 ch = __shfl_sync(kFull, c8, 0) & 255u;
-            io.pos = __shfl_sync(kFull, io.pos, 0);
+            u32 c8 = 1;
+#pragma unroll 1
+            for (int half = 0; half < 2; ++half) {
+                C.probe(c8);
+                code_nibble<NI, MIX2, true>(C, 0, c8, low, high, code, io);
+            }
+            const u32 ch = c8 & 255u;
             C.byte_end(ch);
             if (pp_state == 0) {  // PostProcessor.write state 0 (decompressor.v:58-70)
                 pp_state = ch == 1 ? 2 : 1;
@@ -487,8 +501,6 @@ __global__ void __launch_bounds__(256, 1) k_decode_chain(DecodeArgs A) {
                 }
             }
         }
-        io.pos = __shfl_sync(kFull, io.pos, 0);
-        code = __shfl_sync(kFull, code, 0);
         if (unsupported) { res.status = ZPAQGPU_E_UNSUPPORTED; break; }
         if (staged) {
             __syncwarp();
