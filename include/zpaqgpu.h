@@ -65,6 +65,19 @@ int zpaqgpu_level_header(int level, uint8_t *out, int cap);
  * squash 4096 x int32, stretch 32768 x int32, state table 1024 x uint8 (statetable.v:15-57). */
 int zpaqgpu_tables(int32_t *squash4096, int32_t *stretch32768, uint8_t *state1024);
 
+/* Geometry the library derives from a model header in the levels.v layout, the way
+ * Compressor.start_block (compressor.v:96-145) and Predictor.init (predictor.v:292-470) do. */
+typedef struct {
+    int32_t n, cend, hbegin, hend;   /* components, z.cend, z.hbegin, z.hend                  */
+    int32_t hsize;                   /* the two-byte size written after "zPQ" lvl typ         */
+    int32_t is_chain;                /* 1: ICM + ISSE chain (+MIX2) shape, specialised kernel  */
+    int32_t n_isse, has_mix2;
+    int32_t ctx_mode, n_hash;        /* 0 ZPAQL interpreter, 1 level-1 program, 2 hash chain   */
+    uint64_t workspace_bytes;        /* HBM bytes of model state per resident block            */
+    uint64_t hash_table_bytes;       /* of which ICM/ISSE hash tables                          */
+} zpaqgpu_model_info;
+int zpaqgpu_describe_model(const uint8_t *header, int header_len, zpaqgpu_model_info *out);
+
 /* ---- batch compression: the fast path -------------------------------------------------- */
 /* One ZPAQ block with one segment per input range, exactly the bytes that
  *   Compressor.start_block(level); start_segment(name, comment); for compress(65536) {};

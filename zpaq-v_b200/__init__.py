@@ -6,8 +6,8 @@ codec.py   host mirror of the reference's Compressor / Decompresser / Reader / W
 vshim/     the V-side binding a maintainer of the reference would add (not compilable here)
 """
 from . import binding
-from .binding import Context, ZpaqGpuError, level_header, tables
+from .binding import Context, ZpaqGpuError, describe_model, level_header, tables
 from .codec import Compressor, Decompresser, FileReader, FileWriter
 
-__all__ = ["binding", "Context", "ZpaqGpuError", "level_header", "tables", "Compressor", "Decompresser",
+__all__ = ["binding", "Context", "ZpaqGpuError", "level_header", "tables", "describe_model", "Compressor", "Decompresser",
            "FileReader", "FileWriter"]

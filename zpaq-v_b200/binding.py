@@ -18,8 +18,15 @@ EXPORTS = [
     "zpaqgpu_compress_blocks", "zpaqgpu_compress_blocks_header", "zpaqgpu_compress_blocks_dev",
     "zpaqgpu_find_blocks", "zpaqgpu_decompress_archive", "zpaqgpu_decompress_blocks_dev",
     "zpaqgpu_block_begin", "zpaqgpu_block_begin_header", "zpaqgpu_segment_begin", "zpaqgpu_segment_write",
-    "zpaqgpu_segment_end", "zpaqgpu_block_end", "zpaqgpu_last_stats",
+    "zpaqgpu_segment_end", "zpaqgpu_block_end", "zpaqgpu_last_stats", "zpaqgpu_describe_model",
 ]
+
+
+class ModelInfo(C.Structure):
+    _fields_ = [("n", C.c_int32), ("cend", C.c_int32), ("hbegin", C.c_int32), ("hend", C.c_int32),
+                ("hsize", C.c_int32), ("is_chain", C.c_int32), ("n_isse", C.c_int32), ("has_mix2", C.c_int32),
+                ("ctx_mode", C.c_int32), ("n_hash", C.c_int32), ("workspace_bytes", C.c_uint64),
+                ("hash_table_bytes", C.c_uint64)]
 
 
 class Segment(C.Structure):
@@ -82,6 +89,7 @@ def lib():
     L.zpaqgpu_block_end.argtypes = [vp, vp, C.c_uint64, u64p]
     L.zpaqgpu_block_end.restype = C.c_int64
     L.zpaqgpu_last_stats.argtypes = [vp, C.POINTER(Stats)]
+    L.zpaqgpu_describe_model.argtypes = [C.c_char_p, C.c_int, C.POINTER(ModelInfo)]
     _lib = L
     return L
 
@@ -92,6 +100,14 @@ def level_header(level):
     if n < 0:
         raise ZpaqGpuError(n, "level_header")
     return buf.raw[:n]
+
+
+def describe_model(header):
+    info = ModelInfo()
+    rc = lib().zpaqgpu_describe_model(bytes(header), len(header), C.byref(info))
+    if rc < 0:
+        raise ZpaqGpuError(rc, lib().zpaqgpu_strerror(rc).decode())
+    return {k: getattr(info, k) for k, _ in info._fields_}
 
 
 def tables():

@@ -754,6 +754,22 @@ int zpaqgpu_tables(int32_t *squash4096, int32_t *stretch32768, uint8_t *state102
     return ZPAQGPU_OK;
 }
 
+int zpaqgpu_describe_model(const uint8_t *header, int header_len, zpaqgpu_model_info *out) {
+    if (!out) return ZPAQGPU_E_ARG;
+    Model m;
+    const int rc = model_from_level_layout(header, header_len, m);
+    if (rc) return rc;
+    out->n = m.n, out->cend = m.cend, out->hbegin = m.hbegin, out->hend = m.hend;
+    out->hsize = (m.cend + 1) + (m.hend - m.hbegin + 1);
+    out->is_chain = m.is_chain, out->n_isse = m.n_isse, out->has_mix2 = m.has_mix2;
+    out->ctx_mode = m.ctx_mode, out->n_hash = m.n_hash;
+    out->workspace_bytes = m.ws_bytes;
+    out->hash_table_bytes = 0;
+    for (const CompDesc &c : m.comps)
+        if (c.type == C_ICM || c.type == C_ISSE) out->hash_table_bytes += c.ht_len;
+    return ZPAQGPU_OK;
+}
+
 int zpaqgpu_last_stats(const zpaqgpu_ctx *ctx, zpaqgpu_stats *out) {
     if (!ctx || !out) return ZPAQGPU_E_ARG;
     *out = ctx->stats;
