@@ -1,0 +1,38 @@
+// roundtrip_main.cpp -- the shape of zpaq_test.v:364-384 and cmd/main.v:288-401 over the C++ mirror.
+// Built by tests/test_gpu_cpp_mirror.py on the GPU box:  g++ -Iinclude -Izpaq-v_b200/host ... -lzpaqgpu
+#include <cstdio>
+#include <cstring>
+
+#include "zpaq_gpu.hpp"
+
+int main(int argc, char **argv) {
+    const int level = argc > 1 ? std::atoi(argv[1]) : 1;
+    std::vector<uint8_t> input;
+    for (int c; (c = std::getchar()) != EOF;) input.push_back(uint8_t(c));
+    zpaq::FileReader in(input);
+    zpaq::FileWriter out;
+    zpaq::Compressor comp;
+    comp.set_input(&in);
+    comp.set_output(&out);
+    comp.start_block(level);
+    comp.start_segment("test", "");
+    while (comp.compress(65536)) {}
+    comp.end_segment();
+    comp.end_block();
+    zpaq::FileReader arc(out.bytes());
+    zpaq::FileWriter back;
+    zpaq::Decompresser d;
+    d.set_input(&arc);
+    d.set_output(&back);
+    int segs = 0, ok = 0;
+    while (d.find_block())
+        while (d.find_filename()) {
+            while (d.decompress(65536)) {}
+            d.read_segment_end();
+            ++segs, ok += d.last_sha1_ok() == 1;
+        }
+    const bool same = back.bytes() == input;
+    for (uint8_t b : out.bytes()) std::printf("%02x", b);
+    std::printf("\n%d %d %d\n", segs, ok, same ? 1 : 0);
+    return same && segs == 1 && ok == 1 ? 0 : 1;
+}

@@ -1,0 +1,163 @@
+// zpaq_gpu.hpp -- C++ host mirror of the reference's zpaq.Compressor / zpaq.Decompresser / Reader /
+// Writer (compressor.v:16-413, decompressor.v:170-640, io.v:6-21) over the C ABI of libzpaqgpu.
+// Header-only; link with -lzpaqgpu.  Same method names, argument meaning and silent-error
+// behaviour as the V types, so code written against them ports line for line.
+#pragma once
+#include <cstdint>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "zpaqgpu.h"
+
+namespace zpaq {
+
+struct Reader {                       // io.v:6-12
+    virtual int get() = 0;            // one byte or -1 at EOF
+    virtual ~Reader() = default;
+};
+struct Writer {                       // io.v:15-21
+    virtual void put(int c) = 0;
+    virtual void write(const uint8_t *p, size_t n) { for (size_t i = 0; i < n; ++i) put(p[i]); }
+    virtual ~Writer() = default;
+};
+struct FileReader : Reader {          // io.v:41-78
+    std::vector<uint8_t> data;
+    size_t pos = 0;
+    explicit FileReader(std::vector<uint8_t> d) : data(std::move(d)) {}
+    int get() override { return pos < data.size() ? data[pos++] : -1; }
+};
+struct FileWriter : Writer {          // io.v:80-110
+    std::vector<uint8_t> buf;
+    void put(int c) override { buf.push_back(uint8_t(c)); }
+    void write(const uint8_t *p, size_t n) override { buf.insert(buf.end(), p, p + n); }
+    const std::vector<uint8_t> &bytes() const { return buf; }
+};
+
+class Gpu {                           // one context per GPU; no CPU fallback
+  public:
+    static zpaqgpu_ctx *ctx() {
+        static Gpu g;
+        return g.c_;
+    }
+  private:
+    Gpu() {
+        const int rc = zpaqgpu_init(&c_, -1);
+        if (rc != ZPAQGPU_OK) throw std::runtime_error(zpaqgpu_strerror(rc));
+    }
+    ~Gpu() { zpaqgpu_destroy(c_); }
+    zpaqgpu_ctx *c_ = nullptr;
+};
+
+class Compressor {
+  public:
+    void set_input(Reader *r) { in_ = r; }
+    void set_output(Writer *w) { out_ = w; }
+    void start_block(int level) {                                 // compressor.v:79
+        if (state_ != Start) return;
+        if (zpaqgpu_block_begin(Gpu::ctx(), level) == ZPAQGPU_OK) state_ = Block;
+    }
+    void start_segment(const std::string &filename, const std::string &comment) {   // compressor.v:212
+        if (state_ != Block) return;
+        if (zpaqgpu_segment_begin(Gpu::ctx(), filename.c_str(), comment.c_str()) == ZPAQGPU_OK) state_ = Segment;
+    }
+    bool compress(int n) {                                        // compressor.v:259
+        if (state_ != Segment || !in_) return false;
+        std::vector<uint8_t> buf;
+        buf.reserve(size_t(n > 0 ? n : 0));
+        while (int(buf.size()) < n) {
+            const int c = in_->get();
+            if (c < 0) break;
+            buf.push_back(uint8_t(c));
+        }
+        zpaqgpu_segment_write(Gpu::ctx(), buf.data(), buf.size());
+        return int(buf.size()) == n;
+    }
+    void end_segment() {                                          // compressor.v:357
+        if (state_ != Segment) return;
+        zpaqgpu_segment_end(Gpu::ctx());
+        state_ = Block;
+    }
+    void end_block() {                                            // compressor.v:402
+        if (state_ != Block) return;
+        uint64_t need = 0;
+        zpaqgpu_block_end(Gpu::ctx(), nullptr, 0, &need);
+        std::vector<uint8_t> blk(need);
+        const int64_t n = zpaqgpu_block_end(Gpu::ctx(), blk.data(), need, &need);
+        if (n > 0 && out_) out_->write(blk.data(), size_t(n));
+        state_ = Start;
+    }
+  private:
+    enum { Block, Segment, Start } state_ = Start;                // compressor.v:6-8
+    Reader *in_ = nullptr;
+    Writer *out_ = nullptr;
+};
+
+class Decompresser {
+  public:
+    void set_input(Reader *r) { in_ = r, loaded_ = false; }
+    void set_output(Writer *w) { out_ = w; }
+    bool find_block() {                                           // decompressor.v:219
+        if (!in_) return false;
+        load();
+        while (cursor_ < segs_.size() && segs_[cursor_].block_index <= block_) ++cursor_;
+        if (cursor_ >= segs_.size()) return false;
+        block_ = segs_[cursor_].block_index;
+        state_ = Block;
+        return true;
+    }
+    bool find_filename() {                                        // decompressor.v:350
+        if (state_ != Block) return false;
+        if (cursor_ < segs_.size() && segs_[cursor_].block_index == block_) {
+            cur_ = int(cursor_++), served_ = 0, state_ = Segment;
+            return true;
+        }
+        state_ = Start;
+        return false;
+    }
+    std::string get_filename() const { return cur_ < 0 ? "" : cstr(segs_[size_t(cur_)].name_off); }
+    std::string get_comment() const { return cur_ < 0 ? "" : cstr(segs_[size_t(cur_)].comment_off); }
+    bool decompress(int n = -1) {                                 // decompressor.v:443
+        if (state_ != Segment) return false;
+        const zpaqgpu_segment &s = segs_[size_t(cur_)];
+        const uint64_t left = s.out_len - served_;
+        const uint64_t take = (n < 0 || uint64_t(n) > left) ? left : uint64_t(n);
+        if (take && out_) out_->write(plain_.data() + s.out_off + served_, size_t(take));
+        served_ += take;
+        return n >= 0 && take == uint64_t(n);
+    }
+    void read_segment_end() { if (state_ == Segment) state_ = Block; }   // decompressor.v:590
+    int last_sha1_ok() const { return cur_ < 0 ? -1 : segs_[size_t(cur_)].sha1_ok; }
+  private:
+    void load() {
+        if (loaded_) return;
+        for (int c; (c = in_->get()) >= 0;) arc_.push_back(uint8_t(c));
+        uint64_t cap = arc_.size() * 4 + 65536, need = 0;
+        int seg_cap = 256, nseg = 0;
+        for (;;) {
+            plain_.resize(cap), segs_.resize(size_t(seg_cap));
+            const int rc = zpaqgpu_decompress_archive(Gpu::ctx(), arc_.data(), arc_.size(), plain_.data(), cap, &need,
+                                                      segs_.data(), seg_cap, &nseg);
+            if (rc == ZPAQGPU_E_NOSPACE) { cap = need + 16, seg_cap = nseg + 16; continue; }
+            break;
+        }
+        segs_.resize(size_t(nseg));
+        loaded_ = true;
+    }
+    std::string cstr(uint64_t off) const {
+        size_t e = size_t(off);
+        while (e < arc_.size() && arc_[e]) ++e;
+        return std::string(arc_.begin() + long(off), arc_.begin() + long(e));
+    }
+    enum { Block, Segment, Filename, Start } state_ = Start;      // decompressor.v:6-9
+    Reader *in_ = nullptr;
+    Writer *out_ = nullptr;
+    std::vector<uint8_t> arc_, plain_;
+    std::vector<zpaqgpu_segment> segs_;
+    bool loaded_ = false;
+    int block_ = -1, cur_ = -1;
+    size_t cursor_ = 0;
+    uint64_t served_ = 0;
+};
+
+}  // namespace zpaq
