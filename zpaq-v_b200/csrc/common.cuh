@@ -13,6 +13,7 @@ typedef uint16_t u16;
 typedef uint32_t u32;
 typedef uint64_t u64;
 typedef int32_t i32;
+typedef int64_t i64;
 
 // Constant lookup tables in HBM (copied to shared memory by the chain kernel).
 struct DevTables {
