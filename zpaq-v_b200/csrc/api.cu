@@ -286,8 +286,13 @@ int run_compress(zpaqgpu_ctx *ctx, CompressJob &job) {
             int slots = 0;
             if ((rc = plan_slots(ctx, m, n_blocks, arena_bytes, &slots))) return rc;
             if ((rc = ensure(ctx, ctx->workspace, u64(slots) * m.ws_bytes))) return rc;
-            const int wpc = chain ? pick_warps_per_cta(ctx, m, slots) : 4;
-            ctx->stats.warps_per_cta = wpc;
+            // encoder: three warps per block, as many blocks per CTA as spreads the wave over all SMs
+            int wpc = 4;
+            if (chain) {
+                const int per_sm = (slots + ctx->sm_count - 1) / ctx->sm_count;
+                wpc = std::max(1, std::min(encpipe_max_blocks_per_cta(m), per_sm));
+            }
+            ctx->stats.warps_per_cta = chain ? wpc * 3 : wpc;
             for (int first = 0; first < n_blocks; first += slots) {
                 const int n = std::min(slots, n_blocks - first);
                 CK(cudaEventRecord(ctx->ev[0], st));
@@ -302,7 +307,7 @@ int run_compress(zpaqgpu_ctx *ctx, CompressJob &job) {
                 ea.blocks = d_blocks, ea.segs = d_esegs, ea.pay_len = static_cast<u64 *>(ctx->pay_len.p);
                 ea.first_block = first, ea.n_blocks = n;
                 if (chain) {
-                    if (!launch_encode_chain(m, ea, wpc, st)) {
+                    if (!launch_encode_pipe3(m, ea, wpc, st)) {
                         ctx->err = "no chain kernel instantiation for this model";
                         return ZPAQGPU_E_UNSUPPORTED;
                     }

@@ -39,8 +39,11 @@ struct DecodeArgs {
 __global__ void k_encode_generic(EncodeArgs A);
 __global__ void k_decode_generic(DecodeArgs A);
 
-// specialised ICM + ISSE chain (+ MIX2): returns false when no instantiation fits the model
-bool launch_encode_chain(const Model &m, const EncodeArgs &A, int warps_per_cta, cudaStream_t s);
+// specialised ICM + ISSE chain (+ MIX2): return false when no instantiation fits the model.
+// Encoder (kernels_encpipe.cu): three warps per block; decoder (kernels_chain.cu): one warp per block.
+bool launch_encode_pipe3(const Model &m, const EncodeArgs &A, int blocks_per_cta, cudaStream_t s);
+size_t encpipe_smem_bytes(const Model &m, int blocks_per_cta);
+int encpipe_max_blocks_per_cta(const Model &m);
 bool launch_decode_chain(const Model &m, const DecodeArgs &A, int warps_per_cta, cudaStream_t s);
 size_t chain_smem_bytes(const Model &m, int warps_per_cta);
 int chain_max_warps_per_cta(const Model &m);

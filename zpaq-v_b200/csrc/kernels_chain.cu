@@ -28,7 +28,7 @@ namespace zg {
 namespace {
 
 constexpr int kRing = 256;       // input ring (bytes), power of two
-constexpr int kOutStage = 512;   // encoder output stage (bytes)
+constexpr int kOutStage = 256;   // decoder plaintext stage (bytes)
 constexpr u32 kNoSlot = 0xFFFFFFFFu;
 constexpr unsigned kFull = 0xFFFFFFFFu;
 
@@ -284,12 +284,6 @@ __device__ __forceinline__ u32 code_nibble(Chain<NI, MIX2> &C, u32 nib, u32 &c8,
 }
 
 // ---- byte I/O over the shared-memory stages (all lanes execute, same address) ----
-struct EncIO {
-    u8 *stage;
-    u32 fill;
-    __device__ __forceinline__ void put(u32 b) { stage[fill++] = u8(b); }
-    __device__ __forceinline__ u32 get() { return 0; }
-};
 struct DecIO {
     const u8 *ring;
     u64 pos;
@@ -326,303 +320,6 @@ __device__ __forceinline__ void load_shared_tables(u8 *smem, const DevTables &T)
 }
 
 }  // namespace
-
-// ------------------------------------------------------------------------------------------
-// k_encode_chain
-// ------------------------------------------------------------------------------------------
-template <int NI, bool MIX2>
-__global__ void __launch_bounds__(256, 1) k_encode_chain(EncodeArgs A) {
-    extern __shared__ __align__(16) u8 smem[];
-    load_shared_tables(smem, A.tables);
-    const int wic = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int slot = blockIdx.x * (blockDim.x >> 5) + wic;
-    if (slot >= A.n_blocks) return;
-    Chain<NI, MIX2> C;
-    u8 *ws = A.workspace + u64(slot) * A.model.ws_bytes;
-    C.setup(smem + kSharedTables + size_t(wic) * warp_smem_bytes(NI, MIX2), A.model, ws,
-            reinterpret_cast<const int16_t *>(smem), reinterpret_cast<const u16 *>(smem + 65536),
-            smem + 65536 + 8192);
-    const EncBlock blk = A.blocks[A.first_block + slot];
-    for (u32 s = 0; s < blk.n_seg; ++s) {
-        const EncSeg seg = A.segs[blk.first_seg + s];
-        const u8 *src = A.in + seg.in_off;
-        u8 *dst = A.arena + seg.pay_off;
-        C.segment_reset();
-        u32 low = 1, high = 0xFFFFFFFFu, code = 0;
-        EncIO io{C.stage, 0};
-        u64 written = 0;   // payload bytes already moved (or counted) past the stage
-        u64 filled = 0;    // ring holds plaintext [.., filled)
-        const bool pp = (seg.flags & 1u) != 0;
-        const u64 total = seg.in_len + (pp ? 1 : 0);
-        for (u64 k = 0; k < total; ++k) {
-            u32 c = 0;
-            if (!(pp && k == 0)) {
-                const u64 at = pp ? k - 1 : k;
-                ring_fill(C.ring, src, at, filled, seg.in_len, lane);
-                c = C.ring[at & (kRing - 1)];
-            }
-            // "not EOF" flag: encode(0, p=0) => low += 1 (encoder.v:108)
-            low = low + 1;
-            while ((high ^ low) < 0x1000000u) {
-                io.put(high >> 24);
-                low <<= 8;
-                high = (high << 8) | 0xFFu;
-                if (low == 0) low = 1;
-            }
-#pragma unroll 1
-            for (int half = 0; half < 2; ++half) {
-                u32 c8 = half ? (16u | (c >> 4)) : 1u;
-                C.probe(c8);
-                code_nibble<NI, MIX2, false>(C, half ? (c & 15u) : (c >> 4), c8, low, high, code, io);
-            }
-            C.byte_end(c);
-            // move full 256-byte chunks of coded output to HBM
-            if (io.fill >= 256) {
-                __syncwarp();
-                const u32 fill = io.fill;
-                u32 tail = 0;
-                if (lane + 256 < int(fill)) tail = C.stage[256 + lane];
-                for (int q = lane; q < 256; q += 32)
-                    if (written + q < seg.pay_cap) dst[written + q] = C.stage[q];
-                // a byte emits at most 36 coded bytes, so the tail beyond 256 is < 36 bytes
-                u32 tail2 = 0;
-                if (lane + 288 < int(fill)) tail2 = C.stage[288 + lane];
-                __syncwarp();
-                if (lane + 256 < int(fill)) C.stage[lane] = u8(tail);
-                if (lane + 288 < int(fill)) C.stage[32 + lane] = u8(tail2);
-                __syncwarp();
-                written += 256;
-                io.fill = fill - 256;
-            }
-        }
-        // EOF: encode(1, p=0) then flush the four bytes of high (encoder.v:101-105, :130-139)
-        high = low;
-        while ((high ^ low) < 0x1000000u) {
-            io.put(high >> 24);
-            low <<= 8;
-            high = (high << 8) | 0xFFu;
-            if (low == 0) low = 1;
-        }
-        io.put(high >> 24), io.put((high >> 16) & 255u), io.put((high >> 8) & 255u), io.put(high & 255u);
-        __syncwarp();
-        for (u32 q = lane; q < io.fill; q += 32)
-            if (written + q < seg.pay_cap) dst[written + q] = C.stage[q];
-        __syncwarp();
-        if (lane == 0) A.pay_len[blk.first_seg + s] = written + io.fill;
-    }
-}
-
-// ------------------------------------------------------------------------------------------
-// k_encode_pipe: the encoder as a nibble-skewed systolic pipeline inside one warp.
-//
-// When compressing, every coded bit is known in advance, so component i does not have to wait for
-// the coder before it moves on: all it needs from its predecessor is p[i-1] of the same bit.  Lane
-// i therefore runs component i ONE NIBBLE BEHIND lane i-1 (lane 0: ICM, lanes 1..NI: ISSEs, lane
-// Z=NI+1: MIX2 + arithmetic coder).  In one step every lane codes the four bits of "its" nibble:
-// it reads its own bit-history states, its own table entry, takes p[i-1] of the same bit from what
-// lane i-1 produced one step earlier (one SHFL per bit), and updates its own tables.  The serial
-// ISSE chain of predict() (predictor.v:543-664) is gone from the per-bit critical path: a step
-// costs the same for NI = 1 and NI = 7.  Each component still sees its bits in order with exactly
-// the reference's inputs, so tables, predictions and the coded bytes are unchanged.
-// ------------------------------------------------------------------------------------------
-template <int NI, bool MIX2>
-__global__ void __launch_bounds__(256, 1) k_encode_pipe(EncodeArgs A) {
-    extern __shared__ __align__(16) u8 smem[];
-    load_shared_tables(smem, A.tables);
-    const int wic = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int slot = blockIdx.x * (blockDim.x >> 5) + wic;
-    if (slot >= A.n_blocks) return;
-    constexpr int Z = NI + 1;  // lane (and lag in nibbles) of the coder / MIX2 stage
-    Chain<NI, MIX2> C;
-    u8 *ws = A.workspace + u64(slot) * A.model.ws_bytes;
-    C.setup(smem + kSharedTables + size_t(wic) * warp_smem_bytes(NI, MIX2), A.model, ws,
-            reinterpret_cast<const int16_t *>(smem), reinterpret_cast<const u16 *>(smem + 65536),
-            smem + 65536 + 8192);
-    const int lag = lane < Z ? lane : Z;      // lanes beyond Z shadow the coder lane
-    const int hsel = lane < Z ? lane : Z;     // which HASH round this lane latches (Z: the MIX2 context)
-    const EncBlock blk = A.blocks[A.first_block + slot];
-    for (u32 s = 0; s < blk.n_seg; ++s) {
-        const EncSeg seg = A.segs[blk.first_seg + s];
-        const u8 *src = A.in + seg.in_off;
-        u8 *dst = A.arena + seg.pay_off;
-        C.h = 0;  // pr.reset(): contexts to zero, history and tables stay (predictor.v:827-833)
-        u32 low = 1, high = 0xFFFFFFFFu;
-        EncIO io{C.stage, 0};
-        u64 written = 0, filled = 0;
-        const u32 pp = (seg.flags & 1u) ? 1u : 0u;
-        const i64 total = i64(seg.in_len + pp);   // virtual bytes: [PP byte] data...
-        const i64 NN = total * 2;                 // nibbles
-        u32 c_lane = 0;                           // the byte this lane is working on
-        u32 cz = 0, c8z = 1;                      // the coder's byte and partial byte (uniform)
-        i32 pprev[4] = {0, 0, 0, 0}, pprev2[4] = {0, 0, 0, 0};
-        for (i64 S = 0; S < NN + Z; ++S) {
-            const i64 n = S - lag, nz = S - Z;
-            const bool act = n >= 0 && n < NN, actz = nz >= 0 && nz < NN;
-            const u32 half = u32(n) & 1u, halfz = u32(nz) & 1u;
-            // plaintext ring: lane 0 is the furthest ahead, the coder Z nibbles behind
-            {
-                const i64 ahead = (S >> 1) < total ? (S >> 1) : total - 1;
-                const i64 at = ahead - i64(pp);
-                if (at >= 0) ring_fill(C.ring, src, u64(at), filled, seg.in_len, lane);
-            }
-            if (act && half == 0) {
-                const i64 vb = n >> 1;
-                c_lane = (pp && vb == 0) ? 0u : u32(C.ring[u64(vb - pp) & (kRing - 1)]);
-            }
-            if (actz && halfz == 0) {
-                const i64 vb = nz >> 1;
-                cz = (pp && vb == 0) ? 0u : u32(C.ring[u64(vb - pp) & (kRing - 1)]);
-                c8z = 1;
-                if (MIX2) {  // stage a16[(h + k) & mask], k = 0..255, for the coder's new byte
-                    C.mix_h = __shfl_sync(kFull, C.h, Z);
-                    C.stage_mix();
-                }
-                // "not EOF" flag: encode(0, p=0) => low += 1 (encoder.v:108)
-                low = low + 1;
-                while ((high ^ low) < 0x1000000u) {
-                    io.put(high >> 24);
-                    low <<= 8;
-                    high = (high << 8) | 0xFFu;
-                    if (low == 0) low = 1;
-                }
-            }
-            const u32 c8_0 = half ? (16u | (c_lane >> 4)) : 1u;
-            const u32 nib = half ? (c_lane & 15u) : (c_lane >> 4);
-            const u32 nibz = halfz ? (cz & 15u) : (cz >> 4);
-            const bool work = act && C.owner;
-            if (work) C.probe(c8_0);
-            // ---- four bits ----
-            const uint4 s0 = C.sl;  // the states of a nibble's 15 tree nodes never change before they are read
-            u32 idx = 1;
-            i32 pcur[4];
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const u32 y = (nib >> (3 - k)) & 1u;
-                const u32 sh = (k == 0) ? 8u : (idx & 3u) * 8u;
-                const bool hiword = (k == 3) && (idx & 4u);
-                const u32 word = (k < 2) ? s0.x : (k == 2) ? s0.y : (hiword ? s0.w : s0.z);
-                const u32 st = (word >> sh) & 255u;
-                const int2 e = C.tab[st];
-                const u32 nx = C.nex16[st];
-                const i32 pin = __shfl_up_sync(kFull, pprev[k], 1);
-                // predict (predictor.v:555-563 ICM, :615-631 ISSE)
-                const i32 pis = d_clamp2k((e.x * pin + e.y * 64) >> 16);
-                const i32 pout = lane == 0 ? e.y : pis;
-                pcur[k] = pout;
-                // update (predictor.v:701-709 ICM, :776-791 ISSE)
-                const i32 t = y ? 32767 : 0;
-                const u32 v0 = u32(e.x);
-                const u32 vn = u32(i32(v0) + ((t - i32(v0 >> 8)) >> 2));
-                const i32 spn = C.stretch[d_stretch_idx(i32(vn >> 8))];
-                const i32 err = t - i32(C.squash[d_squash_idx(pout)]);
-                const i32 ix = d_clamp512k(e.x + ((err * pin + 4096) >> 13));
-                const i32 iy = d_clamp512k(e.y + ((err + 16) >> 5));
-                int2 *dstp = work ? &C.tab[st] : &C.dump[lane];
-                *dstp = make_int2(lane == 0 ? i32(vn) : ix, lane == 0 ? spn : iy);
-                // successor state into the slot registers (statetable.v:75-88)
-                const u32 ns = (nx >> (y * 8u)) & 255u;
-                const u32 d = (st ^ ns) << sh;
-                if (k < 2) C.sl.x ^= d;
-                else if (k == 2) C.sl.y ^= d;
-                else if (hiword) C.sl.w ^= d;
-                else C.sl.z ^= d;
-                idx = (idx * 2 + y) & 15u;
-                // ---- coder stage: nibble nz, bit k (uniform over the warp) ----
-                const i32 pb = __shfl_sync(kFull, pprev[k], NI);
-                i32 pf = pb, pa = 0, mw = 0;
-                u32 msel = 0;
-                if (MIX2) {  // predictor.v:586-599
-                    pa = __shfl_sync(kFull, pprev2[k], NI > 0 ? NI - 1 : 0);
-                    msel = c8z & C.mix_sel;
-                    mw = C.a16s[msel];
-                    pf = d_clamp2k((mw * pa + (65536 - mw) * pb) >> 16);
-                }
-                const i32 sqf = C.squash[d_squash_idx(pf)];
-                if (actz) {
-                    const u32 yz = (nibz >> (3 - k)) & 1u;
-                    const u32 mid = coder_mid(low, high, u32(sqf) * 2u + 1u);
-                    if (yz) high = mid; else low = mid + 1;
-                    while ((high ^ low) < 0x1000000u) {
-                        io.put(high >> 24);
-                        low <<= 8;
-                        high = (high << 8) | 0xFFu;
-                        if (low == 0) low = 1;
-                    }
-                    if (MIX2) {  // predictor.v:744-762
-                        const i32 merr = (((yz ? 32767 : 0) - sqf) * C.mix_rate) >> 5;
-                        i32 nw = mw + ((merr * (pa - pb) + 4096) >> 13);
-                        nw = max(0, min(65535, nw));
-                        __syncwarp();
-                        if (lane == Z) {
-                            C.a16s[msel] = u16(nw);
-                            C.a16[(C.mix_h + msel) & C.a16_mask] = u16(nw);
-                        }
-                        __syncwarp();
-                    }
-                    c8z = (c8z << 1) | yz;
-                }
-            }
-#pragma unroll
-            for (int k = 0; k < 4; ++k) pprev2[k] = pprev[k], pprev[k] = pcur[k];
-            if (!work) C.sl = s0;  // idle lanes keep their parked slot untouched
-            // ---- end of this lane's byte: contexts of its next byte (predictor.v:809-818) ----
-            {
-                u32 mine = 0, nh;
-                const u32 c = c_lane;
-                if (C.ctx_mode == CTX_M1) {
-                    u32 a = (0u + c + 512u) * 773u;
-                    a = (a + (C.hist & 255u) + 512u) * 773u;
-                    const u32 h0 = a;
-                    a = (a + ((C.hist >> 8) & 255u) + 512u) * 773u;
-                    a = (a + ((C.hist >> 16) & 255u) + 512u) * 773u;
-                    mine = hsel == 0 ? h0 : (hsel == 1 ? a : 0u);
-                    nh = ((C.hist << 8) | c) & 0xFFFFFFu;
-                } else {
-                    u32 a = c;
-                    for (int r = 0; r < C.n_hash; ++r) {
-                        a = (a + C.hist + 512u) * 773u;
-                        if (r == hsel) mine = a;
-                    }
-                    nh = c;
-                }
-                if (act && half == 1) {
-                    C.h = hsel < C.n_comp ? mine : 0u;
-                    C.hist = nh;
-                }
-            }
-            // move full 256-byte chunks of coded output to HBM
-            if (io.fill >= 256) {
-                __syncwarp();
-                const u32 fill = io.fill;
-                u32 tail = 0, tail2 = 0;
-                if (lane + 256 < int(fill)) tail = C.stage[256 + lane];
-                if (lane + 288 < int(fill)) tail2 = C.stage[288 + lane];
-                for (int q = lane; q < 256; q += 32)
-                    if (written + q < seg.pay_cap) dst[written + q] = C.stage[q];
-                __syncwarp();
-                if (lane + 256 < int(fill)) C.stage[lane] = u8(tail);
-                if (lane + 288 < int(fill)) C.stage[32 + lane] = u8(tail2);
-                __syncwarp();
-                written += 256;
-                io.fill = fill - 256;
-            }
-        }
-        // EOF: encode(1, p=0) then flush the four bytes of high (encoder.v:101-105, :130-139)
-        high = low;
-        while ((high ^ low) < 0x1000000u) {
-            io.put(high >> 24);
-            low <<= 8;
-            high = (high << 8) | 0xFFu;
-            if (low == 0) low = 1;
-        }
-        io.put(high >> 24), io.put((high >> 16) & 255u), io.put((high >> 8) & 255u), io.put(high & 255u);
-        __syncwarp();
-        for (u32 q = lane; q < io.fill; q += 32)
-            if (written + q < seg.pay_cap) dst[written + q] = C.stage[q];
-        __syncwarp();
-        if (lane == 0) A.pay_len[blk.first_seg + s] = written + io.fill;
-    }
-}
 
 // ------------------------------------------------------------------------------------------
 // k_decode_chain
@@ -771,41 +468,24 @@ int chain_max_warps_per_cta(const Model &m) {
 }
 
 template <int NI, bool MIX2>
-static bool launch_pair(bool decode, const EncodeArgs *E, const DecodeArgs *D, int n_blocks, int wpc,
-                        size_t smem, cudaStream_t s) {
-    const int grid = (n_blocks + wpc - 1) / wpc;
-    if (decode) {
-        auto k = k_decode_chain<NI, MIX2>;
-        if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)) != cudaSuccess)
-            return false;
-        k<<<grid, wpc * 32, smem, s>>>(*D);
-    } else {
-        auto k = k_encode_pipe<NI, MIX2>;
-        if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)) != cudaSuccess)
-            return false;
-        k<<<grid, wpc * 32, smem, s>>>(*E);
-    }
+static bool launch_dec(const DecodeArgs &D, int wpc, size_t smem, cudaStream_t s) {
+    const int grid = (D.n_blocks + wpc - 1) / wpc;
+    auto k = k_decode_chain<NI, MIX2>;
+    if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)) != cudaSuccess) return false;
+    k<<<grid, wpc * 32, smem, s>>>(D);
     return true;
 }
 
-static bool dispatch(const Model &m, bool decode, const EncodeArgs *E, const DecodeArgs *D, int n_blocks,
-                     int wpc, cudaStream_t s) {
+bool launch_decode_chain(const Model &m, const DecodeArgs &A, int wpc, cudaStream_t s) {
     if (!m.is_chain) return false;
     const size_t smem = chain_smem_bytes(m, wpc);
 #define ZG_CASE(NI, MX) \
-    if (m.n_isse == NI && m.has_mix2 == MX) return launch_pair<NI, MX>(decode, E, D, n_blocks, wpc, smem, s);
+    if (m.n_isse == NI && m.has_mix2 == MX) return launch_dec<NI, MX>(A, wpc, smem, s);
     ZG_CASE(0, false) ZG_CASE(1, false) ZG_CASE(2, false) ZG_CASE(3, false) ZG_CASE(4, false)
     ZG_CASE(5, false) ZG_CASE(6, false) ZG_CASE(7, false)
     ZG_CASE(2, true) ZG_CASE(3, true) ZG_CASE(4, true) ZG_CASE(5, true) ZG_CASE(6, true) ZG_CASE(7, true)
 #undef ZG_CASE
     return false;
-}
-
-bool launch_encode_chain(const Model &m, const EncodeArgs &A, int wpc, cudaStream_t s) {
-    return dispatch(m, false, &A, nullptr, A.n_blocks, wpc, s);
-}
-bool launch_decode_chain(const Model &m, const DecodeArgs &A, int wpc, cudaStream_t s) {
-    return dispatch(m, true, nullptr, &A, A.n_blocks, wpc, s);
 }
 
 }  // namespace zg

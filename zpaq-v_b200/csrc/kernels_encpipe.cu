@@ -1,0 +1,457 @@
+// kernels_encpipe.cu -- k_encode_pipe3: the compressor's hot kernel.
+//
+// When COMPRESSING, every coded bit is known in advance.  Two consequences the reference's serial
+// loop (compressor.v:277-290 -> encoder.v:111-119 -> predictor.v:536-824) does not use:
+//   (1) the bit-history machinery -- slot probes (find_ht), state reads, next-state writes -- never
+//       looks at a prediction, so it can run ahead of the model;
+//   (2) component i only needs p[i-1] of the SAME bit from its predecessor, not the coder's result,
+//       so the ISSE chain can be a pipeline instead of a dependency inside every bit.
+// One warp issues roughly one dependent integer instruction every 3-4 cycles (ncu, profiles/), so a
+// block's speed is set by the number of instructions ITS warp executes per bit.  The work of one
+// ZPAQ block is therefore split over THREE warps that run concurrently on different schedulers:
+//
+//   H (history)  lane i = hash table of component i.  Per nibble: write the previous slot back,
+//                probe the next one (three 16-byte loads in one 64-byte line, issued together),
+//                read the four bit-history states on the path of the known nibble, store them as
+//                one u32 per (nibble, component), insert the successor states.  Prefetches the
+//                lines of the following byte into L2.
+//   M (model)    lane i = component i, running i nibbles behind lane i-1 (systolic skew).  Per bit:
+//                one 64-bit shared-memory read of its table entry, p[i-1] from the neighbour's
+//                previous step (one SHFL), p[i], squash, update of its own entry.  Lane NI (and
+//                NI-1 for MIX2) publish the final stretch-domain predictions per nibble.
+//   C (coder)    MIX2 (weights staged per byte), squash, 32-bit arithmetic coder in registers,
+//                output staged in shared memory and written to HBM in 256-byte chunks.
+//
+// The three warps exchange data through shared-memory rings of 128 nibbles and meet at one named
+// barrier per tick of 32 nibbles (bar.sync, 96 threads): H works on tick T while M works on T-1 and
+// C on T-2.  Every warp executes the same number of ticks, so the schedule cannot deadlock.
+// Each component still sees its bits in order with exactly the reference's inputs: the coded bytes
+// are identical (tests/test_gpu_parity.py).
+#include "../../include/zpaqgpu.h"
+#include "common.cuh"
+#include "kernels.h"
+
+namespace zg {
+namespace {
+
+constexpr int kTick = 32;     // nibbles per barrier interval
+constexpr int kDepth = 128;   // ring depth in nibbles
+constexpr int kInRing = 512;  // plaintext ring, bytes
+constexpr int kStage = 512;   // coder output stage, bytes
+constexpr u32 kNone = 0xFFFFFFFFu;
+constexpr unsigned kAll = 0xFFFFFFFFu;
+constexpr size_t kTables = 32768 * 2 + 4096 * 2 + 512;
+
+__host__ __device__ constexpr size_t block_smem(int ni, bool mix2) {
+    return size_t(ni + 1) * 2048             // adaptive tables
+           + size_t(kDepth) * (ni + 1) * 4   // state ring: one u32 (4 states) per nibble and component
+           + size_t(kDepth) * 8              // final predictions per nibble (4 x i16)
+           + (mix2 ? size_t(kDepth) * 8 + 512 : 0)  // second MIX2 input per nibble, staged weights
+           + kInRing + kStage;
+}
+
+__device__ __forceinline__ uint4 ld128(const u8 *p) {
+    uint4 v;
+    asm volatile("ld.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+__device__ __forceinline__ void group_barrier(int id) { asm volatile("bar.sync %0, 96;" ::"r"(id) : "memory"); }
+
+struct Views {
+    int2 *tab;
+    u32 *st_ring;
+    uint2 *pf_ring, *pa_ring;
+    u16 *a16s;
+    u8 *in_ring, *stage;
+};
+
+template <int NI, bool MIX2>
+__device__ __forceinline__ Views carve(u8 *p) {
+    Views v;
+    v.tab = reinterpret_cast<int2 *>(p), p += size_t(NI + 1) * 2048;
+    v.st_ring = reinterpret_cast<u32 *>(p), p += size_t(kDepth) * (NI + 1) * 4;
+    v.pf_ring = reinterpret_cast<uint2 *>(p), p += size_t(kDepth) * 8;
+    v.pa_ring = reinterpret_cast<uint2 *>(p), p += MIX2 ? size_t(kDepth) * 8 : 0;
+    v.a16s = reinterpret_cast<u16 *>(p), p += MIX2 ? 512 : 0;
+    v.in_ring = p, p += kInRing;
+    v.stage = p;
+    return v;
+}
+
+// Context hash of component `sel` for the byte that follows byte c (closed forms of the two
+// HCOMP programs of the levels, levels.v:72-87 and :126-139), and the history update.
+struct Ctx {
+    int mode, n_hash, n_comp;
+    u32 hist;  // CTX_M1: previous three bytes; CTX_HASHCHAIN: previous byte
+    __device__ __forceinline__ u32 next(u32 c, int sel, u32 &new_hist) const {
+        u32 mine = 0;
+        if (mode == CTX_M1) {
+            u32 a = (0u + c + 512u) * 773u;
+            a = (a + (hist & 255u) + 512u) * 773u;
+            const u32 h0 = a;
+            a = (a + ((hist >> 8) & 255u) + 512u) * 773u;
+            a = (a + ((hist >> 16) & 255u) + 512u) * 773u;
+            mine = sel == 0 ? h0 : (sel == 1 ? a : 0u);
+            new_hist = ((hist << 8) | c) & 0xFFFFFFu;
+        } else {
+            u32 a = c;
+            for (int r = 0; r < n_hash; ++r) {
+                a = (a + hist + 512u) * 773u;
+                if (r == sel) mine = a;
+            }
+            new_hist = c;
+        }
+        return sel < n_comp ? mine : 0u;
+    }
+};
+
+}  // namespace
+
+template <int NI, bool MIX2>
+__global__ void __launch_bounds__(672, 1) k_encode_pipe3(EncodeArgs A, int blocks_per_cta) {
+    extern __shared__ __align__(16) u8 smem[];
+    {   // squash/stretch/next-state tables, shared by the CTA
+        const uint4 *g = reinterpret_cast<const uint4 *>(A.tables.stretch);
+        uint4 *d = reinterpret_cast<uint4 *>(smem);
+        for (int k = threadIdx.x; k < 4096; k += blockDim.x) d[k] = g[k];
+        const uint4 *g2 = reinterpret_cast<const uint4 *>(A.tables.squash);
+        uint4 *d2 = reinterpret_cast<uint4 *>(smem + 65536);
+        for (int k = threadIdx.x; k < 512; k += blockDim.x) d2[k] = g2[k];
+        for (int k = threadIdx.x; k < 512; k += blockDim.x) smem[65536 + 8192 + k] = A.tables.nex[k];
+    }
+    __syncthreads();
+    const int16_t *stretch = reinterpret_cast<const int16_t *>(smem);
+    const u16 *squash = reinterpret_cast<const u16 *>(smem + 65536);
+    const u16 *nex16 = reinterpret_cast<const u16 *>(smem + 65536 + 8192);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int grp = warp / 3, role = warp % 3;
+    const int slot = blockIdx.x * blocks_per_cta + grp;
+    if (slot >= A.n_blocks) return;
+    const int bar = 1 + grp;
+    const Views V = carve<NI, MIX2>(smem + kTables + size_t(grp) * block_smem(NI, MIX2));
+    const ModelDev &M = A.model;
+    u8 *ws = A.workspace + u64(slot) * M.ws_bytes;
+    constexpr int Z = NI + 1;
+    const bool owner = lane <= NI;
+
+    // role-private state that lives across segments (tables and ZPAQL memory persist, Q17)
+    Ctx cx{M.ctx_mode, M.n_hash, M.n, 0u};
+    // H
+    u8 *ht = nullptr;
+    u32 ht_len = 16, slot_at = kNone;
+    int sizebits = 0;
+    uint4 sl = make_uint4(0, 0, 0, 0);
+    // C
+    u16 *a16 = nullptr;
+    u32 a16_mask = 0, mix_sel = 0;
+    i32 mix_rate = 0;
+    if (role == 0 && owner) {
+        const CompDesc &cd = M.comps[lane];
+        ht = ws + cd.ht_off, ht_len = cd.ht_len, sizebits = cd.a + 2;
+    }
+    if (role == 1) {  // adaptive tables: initial images were written into the workspace
+        const u32 *src0 = reinterpret_cast<const u32 *>(ws + M.comps[0].cm_off);
+        for (int k = lane; k < 256; k += 32) {
+            const u32 v = src0[k];
+            V.tab[k] = make_int2(i32(v), i32(stretch[d_stretch_idx(i32(v >> 8))]));
+        }
+#pragma unroll
+        for (int i = 1; i <= NI; ++i) {
+            const int2 *src = reinterpret_cast<const int2 *>(ws + M.comps[i].cm_off);
+            for (int k = lane; k < 256; k += 32) V.tab[i * 256 + k] = src[k];
+        }
+    }
+    if (MIX2 && role == 2) {
+        const CompDesc &cd = M.comps[NI + 1];
+        a16 = reinterpret_cast<u16 *>(ws + cd.a16_off);
+        a16_mask = cd.a16_len - 1, mix_sel = cd.p[3], mix_rate = i32(cd.p[2]);
+    }
+    int2 *tab = V.tab + (owner ? lane : 0) * 256;
+
+    const EncBlock blk = A.blocks[A.first_block + slot];
+    for (u32 s = 0; s < blk.n_seg; ++s) {
+        const EncSeg seg = A.segs[blk.first_seg + s];
+        const u8 *src = A.in + seg.in_off;
+        const u32 pp = (seg.flags & 1u) ? 1u : 0u;
+        const i64 total = i64(seg.in_len + pp);  // virtual bytes: [PP byte] data...
+        const i64 NN = total * 2;
+        const i64 NT = (NN + 16 + kTick - 1) / kTick + 2;
+        auto vbyte = [&](i64 vb) -> u32 {
+            return (pp && vb == 0) ? 0u : u32(V.in_ring[u64(vb - pp) & (kInRing - 1)]);
+        };
+        // per-segment state
+        u32 h = 0;                       // pr.reset(): contexts to zero (predictor.v:827-833)
+        u64 filled = 0;                  // H: plaintext ring holds [.., filled)
+        i32 pprev[4] = {0, 0, 0, 0};     // M: this lane's predictions of the previous step
+        u32 low = 1, high = 0xFFFFFFFFu; // C
+        u32 fill = 0, cz = 0, c8z = 1, mix_h = 0;
+        u64 written = 0;
+        u8 *dst = A.arena + seg.pay_off;
+        auto put = [&](u32 b) { V.stage[fill++] = u8(b); };
+        group_barrier(bar);  // tables loaded / previous segment drained
+
+        for (i64 T = 0; T < NT; ++T) {
+            if (role == 0) {
+                // ================= H: bit histories =================
+                const i64 n0 = T * kTick, n1 = (n0 + kTick < NN) ? n0 + kTick : NN;
+                u32 c = 0;
+                for (i64 N = n0; N < n1; ++N) {
+                    const i64 vb = N >> 1;
+                    const u32 half = u32(N) & 1u;
+                    if (half == 0) {
+                        const i64 at = vb - i64(pp);
+                        if (at >= 0 && filled < u64(at) + 64) {
+                            __syncwarp();
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) {
+                                const u64 q = filled + u64(lane + 32 * k);
+                                V.in_ring[q & (kInRing - 1)] = q < seg.in_len ? src[q] : u8(0);
+                            }
+                            filled += 128;
+                            __syncwarp();
+                        }
+                        c = vbyte(vb);
+                        // the two lines of the NEXT byte are already determined: pull them into L2
+                        if (owner && vb + 1 < total) {
+                            u32 nh;
+                            const u32 hn = cx.next(c, lane, nh);
+                            const u32 cn = vbyte(vb + 1);
+                            const u32 k0 = hn + 16u, k1 = hn + 16u * (16u | (cn >> 4));
+                            prefetch_l2(ht + (((k0 * 16u) & (ht_len - 16u)) & ~63u));
+                            prefetch_l2(ht + (((k1 * 16u) & (ht_len - 16u)) & ~63u));
+                        }
+                    }
+                    const u32 c8 = half ? (16u | (c >> 4)) : 1u;
+                    const u32 nib = half ? (c & 15u) : (c >> 4);
+                    if (owner) {
+                        // Predictor.find_ht (predictor.v:495-532); the slot of the previous nibble goes
+                        // back first (the reference updates the table in place)
+                        if (slot_at != kNone) *reinterpret_cast<uint4 *>(ht + slot_at) = sl;
+                        const u32 key = h + 16u * c8;
+                        const u32 chk = (key >> sizebits) & 255u;
+                        const u32 h0 = (key * 16u) & (ht_len - 16u), h1 = h0 ^ 16u, h2 = h0 ^ 32u;
+                        const uint4 a0 = ld128(ht + h0), a1 = ld128(ht + h1), a2 = ld128(ht + h2);
+                        const bool m0 = (a0.x & 255u) == chk, m1 = (a1.x & 255u) == chk, m2 = (a2.x & 255u) == chk;
+                        const u32 q0 = (a0.x >> 8) & 255u, q1 = (a1.x >> 8) & 255u, q2 = (a2.x >> 8) & 255u;
+                        const u32 victim = (q0 <= q1 && q0 <= q2) ? h0 : (q1 < q2 ? h1 : h2);
+                        const bool hit = m0 | m1 | m2;
+                        slot_at = m0 ? h0 : m1 ? h1 : m2 ? h2 : victim;
+                        const uint4 pick = m0 ? a0 : (m1 ? a1 : a2);
+                        sl.x = hit ? pick.x : chk, sl.y = hit ? pick.y : 0u;
+                        sl.z = hit ? pick.z : 0u, sl.w = hit ? pick.w : 0u;
+                        // the four states on the path of this nibble, and their successors
+                        const uint4 s0 = sl;
+                        u32 idx = 1, st4 = 0;
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            const u32 y = (nib >> (3 - k)) & 1u;
+                            const u32 sh = (k == 0) ? 8u : (idx & 3u) * 8u;
+                            const bool hiword = (k == 3) && (idx & 4u);
+                            const u32 word = (k < 2) ? s0.x : (k == 2) ? s0.y : (hiword ? s0.w : s0.z);
+                            const u32 st = (word >> sh) & 255u;
+                            st4 |= st << (8 * k);
+                            const u32 ns = (u32(nex16[st]) >> (y * 8u)) & 255u;
+                            const u32 d = (st ^ ns) << sh;
+                            if (k < 2) sl.x ^= d;
+                            else if (k == 2) sl.y ^= d;
+                            else if (hiword) sl.w ^= d;
+                            else sl.z ^= d;
+                            idx = (idx * 2 + y) & 15u;
+                        }
+                        V.st_ring[(u32(N) & (kDepth - 1)) * (NI + 1) + lane] = st4;
+                    }
+                    if (half == 1) {  // contexts of the next byte (predictor.v:809-818)
+                        u32 nh;
+                        h = cx.next(c, lane, nh);
+                        cx.hist = nh;
+                    }
+                }
+            } else if (role == 1) {
+                // ================= M: ICM + ISSE stages, lane i lags i nibbles =================
+                if (T >= 1) {
+                    const i64 s0 = (T - 1) * kTick;
+                    for (i64 S = s0; S < s0 + kTick; ++S) {
+                        const i64 n = S - lane;
+                        const bool act = owner && n >= 0 && n < NN;
+                        u32 st4 = 0, nib = 0;
+                        if (act) {
+                            st4 = V.st_ring[(u32(n) & (kDepth - 1)) * (NI + 1) + lane];
+                            const u32 c = vbyte(n >> 1);
+                            nib = (n & 1) ? (c & 15u) : (c >> 4);
+                        }
+                        i32 pcur[4];
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            const u32 y = (nib >> (3 - k)) & 1u;
+                            const u32 st = (st4 >> (8 * k)) & 255u;
+                            const int2 e = tab[st];
+                            const i32 pin = __shfl_up_sync(kAll, pprev[k], 1);
+                            // predict (predictor.v:555-563 ICM, :615-631 ISSE)
+                            const i32 pis = d_clamp2k((e.x * pin + e.y * 64) >> 16);
+                            const i32 pout = lane == 0 ? e.y : pis;
+                            pcur[k] = pout;
+                            // update (predictor.v:701-709 ICM, :776-791 ISSE)
+                            const i32 t = y ? 32767 : 0;
+                            const u32 v0 = u32(e.x);
+                            const u32 vn = u32(i32(v0) + ((t - i32(v0 >> 8)) >> 2));
+                            const i32 spn = stretch[d_stretch_idx(i32(vn >> 8))];
+                            const i32 err = t - i32(squash[d_squash_idx(pout)]);
+                            const i32 ix = d_clamp512k(e.x + ((err * pin + 4096) >> 13));
+                            const i32 iy = d_clamp512k(e.y + ((err + 16) >> 5));
+                            if (act) tab[st] = make_int2(lane == 0 ? i32(vn) : ix, lane == 0 ? spn : iy);
+                        }
+                        auto pack = [&]() {
+                            uint2 r;
+                            r.x = (u32(pcur[0]) & 0xFFFFu) | (u32(pcur[1]) << 16);
+                            r.y = (u32(pcur[2]) & 0xFFFFu) | (u32(pcur[3]) << 16);
+                            return r;
+                        };
+                        if (act && lane == NI) V.pf_ring[u32(n) & (kDepth - 1)] = pack();
+                        if (MIX2 && act && lane == NI - 1) V.pa_ring[u32(n) & (kDepth - 1)] = pack();
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) pprev[k] = pcur[k];
+                    }
+                }
+            } else {
+                // ================= C: MIX2 + arithmetic coder =================
+                const i64 lo = (T - 2) * kTick - 16;
+                i64 n0 = lo < 0 ? 0 : lo, n1 = lo + kTick;
+                if (n1 > NN) n1 = NN;
+                for (i64 n = n0; n < n1; ++n) {
+                    const u32 half = u32(n) & 1u;
+                    if (half == 0) {
+                        cz = vbyte(n >> 1);
+                        c8z = 1;
+                        if (MIX2) {  // stage a16[(h + k) & mask], k = 0..255, for this byte
+                            mix_h = h;
+                            __syncwarp();
+                            for (int k = lane; k < 256; k += 32) V.a16s[k] = a16[(mix_h + u32(k)) & a16_mask];
+                            __syncwarp();
+                        }
+                        // "not EOF" flag: encode(0, p=0) => low += 1 (encoder.v:108)
+                        low = low + 1;
+                        while ((high ^ low) < 0x1000000u) {
+                            put(high >> 24);
+                            low <<= 8;
+                            high = (high << 8) | 0xFFu;
+                            if (low == 0) low = 1;
+                        }
+                    }
+                    const u32 nibz = half ? (cz & 15u) : (cz >> 4);
+                    const uint2 pf4 = V.pf_ring[u32(n) & (kDepth - 1)];
+                    uint2 pa4 = make_uint2(0, 0);
+                    if (MIX2) pa4 = V.pa_ring[u32(n) & (kDepth - 1)];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const u32 wsel = (k < 2) ? pf4.x : pf4.y;
+                        const i32 pb = i32(int16_t((k & 1) ? (wsel >> 16) : (wsel & 0xFFFFu)));
+                        i32 pf = pb, pa = 0, mw = 0;
+                        u32 msel = 0;
+                        if (MIX2) {  // predictor.v:586-599
+                            const u32 asel = (k < 2) ? pa4.x : pa4.y;
+                            pa = i32(int16_t((k & 1) ? (asel >> 16) : (asel & 0xFFFFu)));
+                            msel = c8z & mix_sel;
+                            mw = V.a16s[msel];
+                            pf = d_clamp2k((mw * pa + (65536 - mw) * pb) >> 16);
+                        }
+                        const i32 sqf = squash[d_squash_idx(pf)];
+                        const u32 yz = (nibz >> (3 - k)) & 1u;
+                        const u32 mid = coder_mid(low, high, u32(sqf) * 2u + 1u);
+                        if (yz) high = mid; else low = mid + 1;
+                        while ((high ^ low) < 0x1000000u) {
+                            put(high >> 24);
+                            low <<= 8;
+                            high = (high << 8) | 0xFFu;
+                            if (low == 0) low = 1;
+                        }
+                        if (MIX2) {  // predictor.v:744-762
+                            const i32 merr = (((yz ? 32767 : 0) - sqf) * mix_rate) >> 5;
+                            i32 nw = mw + ((merr * (pa - pb) + 4096) >> 13);
+                            nw = max(0, min(65535, nw));
+                            __syncwarp();
+                            if (lane == 0) {
+                                V.a16s[msel] = u16(nw);
+                                a16[(mix_h + msel) & a16_mask] = u16(nw);
+                            }
+                            __syncwarp();
+                        }
+                        c8z = (c8z << 1) | yz;
+                    }
+                    if (half == 1) {  // the MIX2 context of the next byte is HASH round NI+1
+                        u32 nh;
+                        h = cx.next(cz, Z, nh);
+                        cx.hist = nh;
+                    }
+                    if (fill >= 256) {  // full 256-byte chunk of coded output to HBM
+                        __syncwarp();
+                        u32 tail = 0, tail2 = 0;
+                        if (lane + 256 < int(fill)) tail = V.stage[256 + lane];
+                        if (lane + 288 < int(fill)) tail2 = V.stage[288 + lane];
+                        for (int q = lane; q < 256; q += 32)
+                            if (written + q < seg.pay_cap) dst[written + q] = V.stage[q];
+                        __syncwarp();
+                        if (lane + 256 < int(fill)) V.stage[lane] = u8(tail);
+                        if (lane + 288 < int(fill)) V.stage[32 + lane] = u8(tail2);
+                        __syncwarp();
+                        written += 256;
+                        fill -= 256;
+                    }
+                }
+            }
+            group_barrier(bar);
+        }
+        if (role == 2) {
+            // EOF: encode(1, p=0) then flush the four bytes of high (encoder.v:101-105, :130-139)
+            high = low;
+            while ((high ^ low) < 0x1000000u) {
+                put(high >> 24);
+                low <<= 8;
+                high = (high << 8) | 0xFFu;
+                if (low == 0) low = 1;
+            }
+            put(high >> 24), put((high >> 16) & 255u), put((high >> 8) & 255u), put(high & 255u);
+            __syncwarp();
+            for (u32 q = lane; q < fill; q += 32)
+                if (written + q < seg.pay_cap) dst[written + q] = V.stage[q];
+            __syncwarp();
+            if (lane == 0) A.pay_len[blk.first_seg + s] = written + fill;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// dispatch
+// ------------------------------------------------------------------------------------------
+size_t encpipe_smem_bytes(const Model &m, int blocks_per_cta) {
+    return kTables + size_t(blocks_per_cta) * block_smem(m.n_isse, m.has_mix2);
+}
+int encpipe_max_blocks_per_cta(const Model &m) {
+    const size_t budget = 227 * 1024;
+    int g = int((budget - kTables) / block_smem(m.n_isse, m.has_mix2));
+    return g > 7 ? 7 : g;
+}
+
+template <int NI, bool MIX2>
+static bool launch_one(const EncodeArgs &A, int g, size_t smem, cudaStream_t s) {
+    auto k = k_encode_pipe3<NI, MIX2>;
+    if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)) != cudaSuccess) return false;
+    const int grid = (A.n_blocks + g - 1) / g;
+    k<<<grid, g * 96, smem, s>>>(A, g);
+    return true;
+}
+
+bool launch_encode_pipe3(const Model &m, const EncodeArgs &A, int blocks_per_cta, cudaStream_t s) {
+    if (!m.is_chain) return false;
+    const size_t smem = encpipe_smem_bytes(m, blocks_per_cta);
+#define ZG_CASE(NI, MX) \
+    if (m.n_isse == NI && m.has_mix2 == MX) return launch_one<NI, MX>(A, blocks_per_cta, smem, s);
+    ZG_CASE(0, false) ZG_CASE(1, false) ZG_CASE(2, false) ZG_CASE(3, false) ZG_CASE(4, false)
+    ZG_CASE(5, false) ZG_CASE(6, false) ZG_CASE(7, false)
+    ZG_CASE(2, true) ZG_CASE(3, true) ZG_CASE(4, true) ZG_CASE(5, true) ZG_CASE(6, true) ZG_CASE(7, true)
+#undef ZG_CASE
+    return false;
+}
+
+}  // namespace zg
