@@ -677,7 +677,7 @@ int zpaqgpu_init(zpaqgpu_ctx **out, int device) {
     ok = ok && cudaEventCreateWithFlags(&ctx->ev_main, cudaEventDisableTiming) == cudaSuccess;
     // constant tables: narrowed on the host, uploaded once
     const Tables &T = tables();
-    const size_t bytes = 32768 * 2 + 4096 * 2 + 512 + 1024 * 4 + 256 * 4;
+    const size_t bytes = 32768 * 2 + 4096 * 2 + 512 + 1024 * 4 + 256 * 4 + 4096 * 2 + 32768 * 2;
     std::vector<uint8_t> img(bytes);
     int16_t *st = reinterpret_cast<int16_t *>(img.data());
     uint16_t *sq = reinterpret_cast<uint16_t *>(img.data() + 65536);
@@ -689,6 +689,14 @@ int zpaqgpu_init(zpaqgpu_ctx **out, int device) {
     for (int s = 0; s < 256; ++s) nx[s * 2] = T.ns[s * 4], nx[s * 2 + 1] = T.ns[s * 4 + 1];
     std::memcpy(dt, T.dt, sizeof(T.dt));
     std::memcpy(d2, T.dt2k, sizeof(T.dt2k));
+    uint16_t *sqp = reinterpret_cast<uint16_t *>(d2 + 256);
+    int16_t *stp = reinterpret_cast<int16_t *>(sqp + 4096);
+    for (int j = 0; j < 4096; ++j) {  // squash(p) for p = j - 2048: index p+2047 clamped to [0,4093]
+        int idx = j - 1;
+        idx = idx < 0 ? 0 : (idx > 4093 ? 4093 : idx);
+        sqp[j] = uint16_t(T.squash[idx]);
+    }
+    for (int i = 0; i < 32768; ++i) stp[i] = int16_t(T.stretch[i < 1 ? 1 : i]);
     ok = ok && cudaMalloc(&ctx->tables_mem, bytes) == cudaSuccess;
     ok = ok && cudaMemcpy(ctx->tables_mem, img.data(), bytes, cudaMemcpyHostToDevice) == cudaSuccess;
     if (!ok) {
@@ -702,6 +710,8 @@ int zpaqgpu_init(zpaqgpu_ctx **out, int device) {
     ctx->tables.nex = base + 65536 + 8192;
     ctx->tables.dt = reinterpret_cast<const i32 *>(base + 65536 + 8192 + 512);
     ctx->tables.dt2k = ctx->tables.dt + 1024;
+    ctx->tables.squash_pad = reinterpret_cast<const u16 *>(ctx->tables.dt2k + 256);
+    ctx->tables.stretch_pad = reinterpret_cast<const int16_t *>(ctx->tables.squash_pad + 4096);
     *out = ctx;
     return ZPAQGPU_OK;
 }

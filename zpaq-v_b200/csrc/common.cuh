@@ -19,6 +19,9 @@ typedef int64_t i64;
 struct DevTables {
     const int16_t *stretch;  // 32768 entries, stretch_table narrowed to i16 (range +-2047)
     const u16 *squash;       // 4096 entries, squash_table narrowed to u16 (range 1..32767)
+    const u16 *squash_pad;   // 4096 entries indexed by p+2048 for p in [-2048,2047]: the index clamp of
+                             // squash() (predictor.v:193-202) folded into the table
+    const int16_t *stretch_pad;  // stretch with entry 0 := entry 1 (stretch() clamps its index to >= 1)
     const u8 *nex;           // 512 entries: nex[s*2+y] = next state (statetable.v ns[s*4+y])
     const i32 *dt;           // 1024 entries (CM)
     const i32 *dt2k;         // 256 entries (MATCH)
@@ -81,6 +84,8 @@ __device__ __forceinline__ i32 d_clamp512k(i32 x) { return max(-262144, min(2621
 __device__ __forceinline__ i32 d_squash_idx(i32 d) { return max(0, min(4093, d + 2047)); }
 // stretch index: clamped to [1,32767]
 __device__ __forceinline__ i32 d_stretch_idx(i32 p) { return max(1, min(32767, p)); }
+// index into stretch_pad for a non-negative argument (entry 0 already holds entry 1)
+__device__ __forceinline__ u32 d_stretch_pad_idx(u32 p) { return min(p, 32767u); }
 
 // ---- binary arithmetic coder state (encoder.v:48-89, decoder.v:73-118) ----
 // mid = low + ((high-low)*p >> 16) with p < 65536: one IMAD.HI on (p << 16).

@@ -49,8 +49,8 @@ __device__ __forceinline__ uint4 ldg128(const u8 *p) {
 template <int NI, bool MIX2>
 struct Chain {
     // shared-memory views
-    const int16_t *stretch;
-    const u16 *squash;
+    const int16_t *stretch;  // padded: entry 0 holds entry 1
+    const u16 *squash;       // padded: indexed by p + 2048
     const u16 *nex16;  // nex16[s] = next(s,0) | next(s,1) << 8
     int2 *tab;         // this lane's table: ICM {cm[s], stretch(cm[s]>>8)} or ISSE {wt0, wt1}
     int2 *dump;        // 32 entries nobody reads
@@ -92,7 +92,7 @@ struct Chain {
         const u32 *src0 = reinterpret_cast<const u32 *>(ws + M.comps[0].cm_off);
         for (int k = lane; k < 256; k += 32) {
             const u32 v = src0[k];
-            tables[k] = make_int2(i32(v), i32(st[d_stretch_idx(i32(v >> 8))]));
+            tables[k] = make_int2(i32(v), i32(st[d_stretch_pad_idx(v >> 8)]));
         }
 #pragma unroll
         for (int i = 1; i <= NI; ++i) {
@@ -130,29 +130,36 @@ struct Chain {
         }
     }
 
-    // After byte c: run the HCOMP program in closed form (levels.v:72-87, :126-139) and latch the
-    // hash of this lane's component (predictor.v:809-818).
-    __device__ void byte_end(u32 c) {
-        u32 mine = 0, mixv = 0;
+    // HCOMP in closed form (levels.v:72-87, :126-139): the context hash component `sel` gets for
+    // the byte that follows byte c.
+    __device__ __forceinline__ u32 ctx_next(u32 c, int sel, u32 &new_hist, u32 &mixv) const {
+        u32 mine = 0;
+        mixv = 0;
         if (ctx_mode == CTX_M1) {
             u32 a = (0u + c + 512u) * 773u;
             a = (a + (hist & 255u) + 512u) * 773u;
             const u32 h0 = a;
             a = (a + ((hist >> 8) & 255u) + 512u) * 773u;
             a = (a + ((hist >> 16) & 255u) + 512u) * 773u;
-            mine = lane == 0 ? h0 : (lane == 1 ? a : 0u);
-            hist = ((hist << 8) | c) & 0xFFFFFFu;
+            mine = sel == 0 ? h0 : (sel == 1 ? a : 0u);
+            new_hist = ((hist << 8) | c) & 0xFFFFFFu;
         } else {
             u32 a = c;
-            const u32 q = hist;
             for (int r = 0; r < n_hash; ++r) {
-                a = (a + q + 512u) * 773u;
-                if (r == lane) mine = a;
+                a = (a + hist + 512u) * 773u;
+                if (r == sel) mine = a;
                 if (MIX2 && r == NI + 1) mixv = a;
             }
-            hist = c;
+            new_hist = c;
         }
-        h = lane < n_comp ? mine : 0u;
+        return sel < n_comp ? mine : 0u;
+    }
+
+    // After byte c: latch the hash of this lane's component (predictor.v:809-818).
+    __device__ void byte_end(u32 c) {
+        u32 nh, mixv;
+        h = ctx_next(c, lane, nh, mixv);
+        hist = nh;
         if (MIX2) {
             mix_h = mixv;
             stage_mix();
@@ -215,7 +222,7 @@ __device__ __forceinline__ u32 code_nibble(Chain<NI, MIX2> &C, u32 nib, u32 &c8,
         const u32 v0 = u32(e.x);
         const i32 r0 = i32(v0 >> 8);
         const u32 va = u32(i32(v0) + ((0 - r0) >> 2)), vb = u32(i32(v0) + ((32767 - r0) >> 2));
-        const i32 spa = C.stretch[d_stretch_idx(i32(va >> 8))], spb = C.stretch[d_stretch_idx(i32(vb >> 8))];
+        const i32 spa = C.stretch[d_stretch_pad_idx(va >> 8)], spb = C.stretch[d_stretch_pad_idx(vb >> 8)];
         // ---- predict: all-gather the weights, evaluate the ISSE chain on every lane ----
         i32 p = __shfl_sync(kFull, e.y, 0);  // p[0] = stretch(cm[state] >> 8)
         i32 pin = 0, pout = p, pa = 0, pb = 0;
@@ -229,8 +236,8 @@ __device__ __forceinline__ u32 code_nibble(Chain<NI, MIX2> &C, u32 nib, u32 &c8,
             p = pn;
         }
         if (MIX2) p = d_clamp2k((mw * pa + (65536 - mw) * pb) >> 16);
-        const i32 sq_own = C.squash[d_squash_idx(pout)];
-        const i32 sq_fin = C.squash[d_squash_idx(p)];
+        const i32 sq_own = C.squash[pout + 2048];
+        const i32 sq_fin = C.squash[p + 2048];
         const u32 p16 = u32(sq_fin) * 2u + 1u;
         // ---- code ----
         const u32 mid = coder_mid(low, high, p16);
@@ -308,10 +315,10 @@ __device__ __forceinline__ void ring_fill(u8 *ring, const u8 *base, u64 pos, u64
 }
 
 __device__ __forceinline__ void load_shared_tables(u8 *smem, const DevTables &T) {
-    const uint4 *g = reinterpret_cast<const uint4 *>(T.stretch);
+    const uint4 *g = reinterpret_cast<const uint4 *>(T.stretch_pad);
     uint4 *d = reinterpret_cast<uint4 *>(smem);
     for (int k = threadIdx.x; k < 4096; k += blockDim.x) d[k] = g[k];
-    const uint4 *g2 = reinterpret_cast<const uint4 *>(T.squash);
+    const uint4 *g2 = reinterpret_cast<const uint4 *>(T.squash_pad);
     uint4 *d2 = reinterpret_cast<uint4 *>(smem + 65536);
     for (int k = threadIdx.x; k < 512; k += blockDim.x) d2[k] = g2[k];
     u8 *s_nex = smem + 65536 + 8192;

@@ -47,7 +47,8 @@ __host__ __device__ constexpr size_t block_smem(int ni, bool mix2) {
            + size_t(kDepth) * (ni + 1) * 4   // state ring: one u32 (4 states) per nibble and component
            + size_t(kDepth) * 8              // final predictions per nibble (4 x i16)
            + (mix2 ? size_t(kDepth) * 8 + 512 : 0)  // second MIX2 input per nibble, staged weights
-           + kInRing + kStage;
+           + kInRing + kStage
+           + 256;                            // store sink of idle M lanes
 }
 
 __device__ __forceinline__ uint4 ld128(const u8 *p) {
@@ -64,6 +65,7 @@ struct Views {
     uint2 *pf_ring, *pa_ring;
     u16 *a16s;
     u8 *in_ring, *stage;
+    int2 *sink;
 };
 
 template <int NI, bool MIX2>
@@ -75,7 +77,8 @@ __device__ __forceinline__ Views carve(u8 *p) {
     v.pa_ring = reinterpret_cast<uint2 *>(p), p += MIX2 ? size_t(kDepth) * 8 : 0;
     v.a16s = reinterpret_cast<u16 *>(p), p += MIX2 ? 512 : 0;
     v.in_ring = p, p += kInRing;
-    v.stage = p;
+    v.stage = p, p += kStage;
+    v.sink = reinterpret_cast<int2 *>(p);
     return v;
 }
 
@@ -112,10 +115,10 @@ template <int NI, bool MIX2>
 __global__ void __launch_bounds__(672, 1) k_encode_pipe3(EncodeArgs A, int blocks_per_cta) {
     extern __shared__ __align__(16) u8 smem[];
     {   // squash/stretch/next-state tables, shared by the CTA
-        const uint4 *g = reinterpret_cast<const uint4 *>(A.tables.stretch);
+        const uint4 *g = reinterpret_cast<const uint4 *>(A.tables.stretch_pad);
         uint4 *d = reinterpret_cast<uint4 *>(smem);
         for (int k = threadIdx.x; k < 4096; k += blockDim.x) d[k] = g[k];
-        const uint4 *g2 = reinterpret_cast<const uint4 *>(A.tables.squash);
+        const uint4 *g2 = reinterpret_cast<const uint4 *>(A.tables.squash_pad);
         uint4 *d2 = reinterpret_cast<uint4 *>(smem + 65536);
         for (int k = threadIdx.x; k < 512; k += blockDim.x) d2[k] = g2[k];
         for (int k = threadIdx.x; k < 512; k += blockDim.x) smem[65536 + 8192 + k] = A.tables.nex[k];
@@ -155,7 +158,7 @@ __global__ void __launch_bounds__(672, 1) k_encode_pipe3(EncodeArgs A, int block
         const u32 *src0 = reinterpret_cast<const u32 *>(ws + M.comps[0].cm_off);
         for (int k = lane; k < 256; k += 32) {
             const u32 v = src0[k];
-            V.tab[k] = make_int2(i32(v), i32(stretch[d_stretch_idx(i32(v >> 8))]));
+            V.tab[k] = make_int2(i32(v), i32(stretch[d_stretch_pad_idx(v >> 8)]));
         }
 #pragma unroll
         for (int i = 1; i <= NI; ++i) {
@@ -213,12 +216,16 @@ __global__ void __launch_bounds__(672, 1) k_encode_pipe3(EncodeArgs A, int block
                             __syncwarp();
                         }
                         c = vbyte(vb);
-                        // the two lines of the NEXT byte are already determined: pull them into L2
-                        if (owner && vb + 1 < total) {
-                            u32 nh;
-                            const u32 hn = cx.next(c, lane, nh);
-                            const u32 cn = vbyte(vb + 1);
-                            const u32 k0 = hn + 16u, k1 = hn + 16u * (16u | (cn >> 4));
+                        // the two lines byte vb+2 will touch are already determined: pull them into L2
+                        // (two bytes of lead cover an HBM round trip even when this warp runs alone)
+                        if (owner && vb + 2 < total) {
+                            u32 nh1, nh2;
+                            (void)cx.next(c, lane, nh1);
+                            Ctx ahead = cx;
+                            ahead.hist = nh1;
+                            const u32 hn = ahead.next(vbyte(vb + 1), lane, nh2);
+                            const u32 c2 = vbyte(vb + 2);
+                            const u32 k0 = hn + 16u, k1 = hn + 16u * (16u | (c2 >> 4));
                             prefetch_l2(ht + (((k0 * 16u) & (ht_len - 16u)) & ~63u));
                             prefetch_l2(ht + (((k1 * 16u) & (ht_len - 16u)) & ~63u));
                         }
@@ -272,14 +279,21 @@ __global__ void __launch_bounds__(672, 1) k_encode_pipe3(EncodeArgs A, int block
                 // ================= M: ICM + ISSE stages, lane i lags i nibbles =================
                 if (T >= 1) {
                     const i64 s0 = (T - 1) * kTick;
-                    for (i64 S = s0; S < s0 + kTick; ++S) {
-                        const i64 n = S - lane;
-                        const bool act = owner && n >= 0 && n < NN;
+                    // 32-bit window arithmetic: nibble n = s0 + r, r = step - lane
+                    const i32 r_lo = s0 >= 64 ? -64 : i32(-s0);
+                    const i32 r_hi = (NN - s0) > 64 ? 64 : i32(NN - s0);
+                    const u32 base = u32(s0);
+                    int2 *sink = V.sink + lane;
+                    for (int q = 0; q < kTick; ++q) {
+                        const i32 r = q - lane;
+                        const bool act = owner && r >= r_lo && r < r_hi;
+                        const u32 n = base + u32(r);
                         u32 st4 = 0, nib = 0;
                         if (act) {
-                            st4 = V.st_ring[(u32(n) & (kDepth - 1)) * (NI + 1) + lane];
-                            const u32 c = vbyte(n >> 1);
-                            nib = (n & 1) ? (c & 15u) : (c >> 4);
+                            st4 = V.st_ring[(n & (kDepth - 1)) * (NI + 1) + lane];
+                            const u32 vb = n >> 1;
+                            const u32 c = (pp && vb == 0) ? 0u : u32(V.in_ring[(vb - pp) & (kInRing - 1)]);
+                            nib = (n & 1u) ? (c & 15u) : (c >> 4);
                         }
                         i32 pcur[4];
 #pragma unroll
@@ -292,24 +306,25 @@ __global__ void __launch_bounds__(672, 1) k_encode_pipe3(EncodeArgs A, int block
                             const i32 pis = d_clamp2k((e.x * pin + e.y * 64) >> 16);
                             const i32 pout = lane == 0 ? e.y : pis;
                             pcur[k] = pout;
-                            // update (predictor.v:701-709 ICM, :776-791 ISSE)
+                            // update (predictor.v:701-709 ICM, :776-791 ISSE); idle lanes store into a sink
                             const i32 t = y ? 32767 : 0;
                             const u32 v0 = u32(e.x);
                             const u32 vn = u32(i32(v0) + ((t - i32(v0 >> 8)) >> 2));
-                            const i32 spn = stretch[d_stretch_idx(i32(vn >> 8))];
-                            const i32 err = t - i32(squash[d_squash_idx(pout)]);
+                            const i32 spn = stretch[d_stretch_pad_idx(vn >> 8)];
+                            const i32 err = t - i32(squash[pout + 2048]);
                             const i32 ix = d_clamp512k(e.x + ((err * pin + 4096) >> 13));
                             const i32 iy = d_clamp512k(e.y + ((err + 16) >> 5));
-                            if (act) tab[st] = make_int2(lane == 0 ? i32(vn) : ix, lane == 0 ? spn : iy);
+                            int2 *dstp = act ? &tab[st] : sink;
+                            *dstp = make_int2(lane == 0 ? i32(vn) : ix, lane == 0 ? spn : iy);
                         }
                         auto pack = [&]() {
-                            uint2 r;
-                            r.x = (u32(pcur[0]) & 0xFFFFu) | (u32(pcur[1]) << 16);
-                            r.y = (u32(pcur[2]) & 0xFFFFu) | (u32(pcur[3]) << 16);
-                            return r;
+                            uint2 rr;
+                            rr.x = (u32(pcur[0]) & 0xFFFFu) | (u32(pcur[1]) << 16);
+                            rr.y = (u32(pcur[2]) & 0xFFFFu) | (u32(pcur[3]) << 16);
+                            return rr;
                         };
-                        if (act && lane == NI) V.pf_ring[u32(n) & (kDepth - 1)] = pack();
-                        if (MIX2 && act && lane == NI - 1) V.pa_ring[u32(n) & (kDepth - 1)] = pack();
+                        if (act && lane == NI) V.pf_ring[n & (kDepth - 1)] = pack();
+                        if (MIX2 && act && lane == NI - 1) V.pa_ring[n & (kDepth - 1)] = pack();
 #pragma unroll
                         for (int k = 0; k < 4; ++k) pprev[k] = pcur[k];
                     }
@@ -356,7 +371,7 @@ __global__ void __launch_bounds__(672, 1) k_encode_pipe3(EncodeArgs A, int block
                             mw = V.a16s[msel];
                             pf = d_clamp2k((mw * pa + (65536 - mw) * pb) >> 16);
                         }
-                        const i32 sqf = squash[d_squash_idx(pf)];
+                        const i32 sqf = squash[pf + 2048];
                         const u32 yz = (nibz >> (3 - k)) & 1u;
                         const u32 mid = coder_mid(low, high, u32(sqf) * 2u + 1u);
                         if (yz) high = mid; else low = mid + 1;
