@@ -44,6 +44,14 @@ enum {
  * header has that shape (all of -m1..-m5 do) and the generic all-components kernel otherwise. */
 enum { ZPAQGPU_KERNEL_AUTO = 0, ZPAQGPU_KERNEL_GENERIC = 1, ZPAQGPU_KERNEL_CHAIN = 2 };
 
+/* Where the ICM/ISSE hash tables of resident blocks live.  DENSE: the reference's layout, 64<<sizebits
+ * bytes per component and block (predictor.v:359-362).  PAGED: a page table per block and 256-byte
+ * pages from a pool shared by the wave, mapped on first touch -- same bytes in, same bytes out, but
+ * a block costs what it touches (text at -m5: megabytes instead of 2 GiB).  AUTO pages when the
+ * dense tables of the batch do not fit in one wave; if the pool runs dry the call falls back to
+ * dense waves by itself. */
+enum { ZPAQGPU_TABLES_AUTO = 0, ZPAQGPU_TABLES_DENSE = 1, ZPAQGPU_TABLES_PAGED = 2 };
+
 /* ---- lifetime -------------------------------------------------------------------------- */
 /* device < 0 selects the current CUDA device.  Replaces Compressor.new()/Decompresser.new()
  * (compressor.v:33, decompressor.v:187) as the owner of all codec state. */
@@ -54,6 +62,7 @@ const char *zpaqgpu_last_error(const zpaqgpu_ctx *ctx);
 /* Optional tuning: kernel family (above), workspace budget in bytes (0 = 80% of free HBM),
  * CUDA stream to run on (0 = the ctx's own stream). */
 int zpaqgpu_set_kernel(zpaqgpu_ctx *ctx, int kernel);
+int zpaqgpu_set_table_mode(zpaqgpu_ctx *ctx, int mode);
 int zpaqgpu_set_workspace_limit(zpaqgpu_ctx *ctx, uint64_t bytes);
 int zpaqgpu_set_stream(zpaqgpu_ctx *ctx, void *cuda_stream);
 
@@ -167,6 +176,9 @@ typedef struct {
     int32_t kernel;    /* ZPAQGPU_KERNEL_GENERIC or _CHAIN actually used */
     int32_t warps_per_cta;
     uint64_t workspace_bytes_per_block;
+    uint64_t pool_bytes_used; /* paged tables: bytes of pool pages mapped by the largest wave */
+    int32_t paged;            /* 1 when the last call used paged tables                        */
+    int32_t reserved;
 } zpaqgpu_stats;
 int zpaqgpu_last_stats(const zpaqgpu_ctx *ctx, zpaqgpu_stats *out);
 

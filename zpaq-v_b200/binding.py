@@ -11,9 +11,11 @@ LIB_PATH = os.path.join(_HERE, "libzpaqgpu.so")
 
 OK, E_NODEVICE, E_CUDA, E_NOSPACE, E_ARG, E_FORMAT, E_UNSUPPORTED, E_STATE, E_NOMEM = 0, -1, -2, -3, -4, -5, -6, -7, -8
 KERNEL_AUTO, KERNEL_GENERIC, KERNEL_CHAIN = 0, 1, 2
+TABLES_AUTO, TABLES_DENSE, TABLES_PAGED = 0, 1, 2
 
 EXPORTS = [
     "zpaqgpu_init", "zpaqgpu_destroy", "zpaqgpu_strerror", "zpaqgpu_last_error", "zpaqgpu_set_kernel",
+    "zpaqgpu_set_table_mode",
     "zpaqgpu_set_workspace_limit", "zpaqgpu_set_stream", "zpaqgpu_level_header", "zpaqgpu_tables",
     "zpaqgpu_compress_blocks", "zpaqgpu_compress_blocks_header", "zpaqgpu_compress_blocks_dev",
     "zpaqgpu_find_blocks", "zpaqgpu_decompress_archive", "zpaqgpu_decompress_blocks_dev",
@@ -39,7 +41,8 @@ class Stats(C.Structure):
     _fields_ = [("init_ms", C.c_float), ("codec_ms", C.c_float), ("sha1_ms", C.c_float), ("pack_ms", C.c_float),
                 ("h2d_ms", C.c_float), ("d2h_ms", C.c_float), ("launches", C.c_int32),
                 ("codec_launches", C.c_int32), ("waves", C.c_int32), ("retries", C.c_int32), ("kernel", C.c_int32),
-                ("warps_per_cta", C.c_int32), ("workspace_bytes_per_block", C.c_uint64)]
+                ("warps_per_cta", C.c_int32), ("workspace_bytes_per_block", C.c_uint64),
+                ("pool_bytes_used", C.c_uint64), ("paged", C.c_int32), ("reserved", C.c_int32)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -71,6 +74,7 @@ def lib():
     L.zpaqgpu_last_error.argtypes = [vp]
     L.zpaqgpu_last_error.restype = C.c_char_p
     L.zpaqgpu_set_kernel.argtypes = [vp, C.c_int]
+    L.zpaqgpu_set_table_mode.argtypes = [vp, C.c_int]
     L.zpaqgpu_set_workspace_limit.argtypes = [vp, C.c_uint64]
     L.zpaqgpu_set_stream.argtypes = [vp, vp]
     L.zpaqgpu_level_header.argtypes = [C.c_int, C.c_char_p, C.c_int]
@@ -148,6 +152,10 @@ class Context:
 
     def set_kernel(self, kernel):
         self._check(lib().zpaqgpu_set_kernel(self._h, kernel))
+
+    def set_table_mode(self, mode):
+        """0 auto, 1 dense, 2 paged (include/zpaqgpu.h ZPAQGPU_TABLES_*)."""
+        self._check(lib().zpaqgpu_set_table_mode(self._h, mode))
 
     def set_workspace_limit(self, nbytes):
         self._check(lib().zpaqgpu_set_workspace_limit(self._h, nbytes))

@@ -43,13 +43,14 @@ struct zpaqgpu_ctx {
     DevTables tables{};
     void *tables_mem = nullptr;
     int kernel_pref = ZPAQGPU_KERNEL_AUTO;
+    int table_mode = ZPAQGPU_TABLES_AUTO;
     u64 ws_limit = 0;
     int sm_count = 148;
     std::string err;
     zpaqgpu_stats stats{};
     // grow-only device buffers
     DevBuf workspace, in, arena, out, desc, pay_len, digests, seg_size, out_off, modelblob, results,
-        seg_recs, misc, heads, plain;
+        seg_recs, misc, heads, plain, pool;
     // pinned host staging for small read-backs
     void *pinned = nullptr;
     size_t pinned_cap = 0;
@@ -106,53 +107,129 @@ int ensure_pinned(zpaqgpu_ctx *ctx, size_t bytes) {
 
 u64 align_up(u64 v, u64 a) { return (v + a - 1) / a * a; }
 
-// Upload the model (header bytes + component table) and return the device view.
-int upload_model(zpaqgpu_ctx *ctx, const Model &m, ModelDev &md, const FillRegion **d_fills,
-                 const u32 **d_image) {
-    const size_t hdr_bytes = align_up(m.header.size() + 1, 16);
-    const size_t comp_bytes = align_up(sizeof(CompDesc) * std::max<size_t>(1, m.comps.size()), 16);
-    const size_t fill_bytes = align_up(sizeof(FillRegion) * std::max<size_t>(1, m.fills.size()), 16);
-    const size_t img_bytes = align_up(4 * std::max<size_t>(1, m.image.size()), 16);
-    const size_t total = hdr_bytes + comp_bytes + fill_bytes + img_bytes;
+// The model on the device: header bytes, both component layouts, their fill lists, the images.
+struct ModelOnDev {
+    ModelDev dense, paged;
+    const FillRegion *fills_dense = nullptr, *fills_paged = nullptr;
+    int n_fills_dense = 0, n_fills_paged = 0;
+    const u32 *image = nullptr;
+};
+
+int upload_model(zpaqgpu_ctx *ctx, const Model &m, ModelOnDev &out) {
+    auto pad = [](size_t v) { return align_up(v, 16); };
+    const size_t n_c = std::max<size_t>(1, m.comps.size());
+    const size_t o_hdr = 0;
+    const size_t o_cd = pad(o_hdr + m.header.size() + 1);
+    const size_t o_cp = pad(o_cd + sizeof(CompDesc) * n_c);
+    const size_t o_fd = pad(o_cp + sizeof(CompDesc) * n_c);
+    const size_t o_fp = pad(o_fd + sizeof(FillRegion) * std::max<size_t>(1, m.fills.size()));
+    const size_t o_im = pad(o_fp + sizeof(FillRegion) * std::max<size_t>(1, m.fills_paged.size()));
+    const size_t total = pad(o_im + 4 * std::max<size_t>(1, m.image.size()));
     int rc = ensure(ctx, ctx->modelblob, total);
     if (rc) return rc;
     std::vector<uint8_t> blob(total, 0);
-    std::memcpy(blob.data(), m.header.data(), m.header.size());
-    if (!m.comps.empty()) std::memcpy(blob.data() + hdr_bytes, m.comps.data(), sizeof(CompDesc) * m.comps.size());
-    if (!m.fills.empty())
-        std::memcpy(blob.data() + hdr_bytes + comp_bytes, m.fills.data(), sizeof(FillRegion) * m.fills.size());
-    if (!m.image.empty())
-        std::memcpy(blob.data() + hdr_bytes + comp_bytes + fill_bytes, m.image.data(), 4 * m.image.size());
+    auto put = [&](size_t at, const void *p, size_t n) { if (n) std::memcpy(blob.data() + at, p, n); };
+    put(o_hdr, m.header.data(), m.header.size());
+    put(o_cd, m.comps.data(), sizeof(CompDesc) * m.comps.size());
+    put(o_cp, m.comps_paged.data(), sizeof(CompDesc) * m.comps_paged.size());
+    put(o_fd, m.fills.data(), sizeof(FillRegion) * m.fills.size());
+    put(o_fp, m.fills_paged.data(), sizeof(FillRegion) * m.fills_paged.size());
+    put(o_im, m.image.data(), 4 * m.image.size());
     // the blob of the previous launch may still be in use by queued kernels
     CK(cudaStreamSynchronize(ctx->stream));
     CK(cudaMemcpyAsync(ctx->modelblob.p, blob.data(), total, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     u8 *base = static_cast<u8 *>(ctx->modelblob.p);
+    ModelDev md{};
     md.n = m.n, md.cend = m.cend, md.hbegin = m.hbegin, md.hend = m.hend, md.header_len = int(m.header.size());
     md.h_len = m.h_len, md.m_len = m.m_len;
     md.h_off = m.h_off, md.m_off = m.m_off, md.r_off = m.r_off, md.rt_off = m.rt_off;
     md.ws_bytes = m.ws_bytes;
-    md.header = base;
-    md.comps = reinterpret_cast<const CompDesc *>(base + hdr_bytes);
+    md.header = base + o_hdr;
+    md.comps = reinterpret_cast<const CompDesc *>(base + o_cd);
     md.ctx_mode = m.ctx_mode, md.n_hash = m.n_hash;
-    *d_fills = reinterpret_cast<const FillRegion *>(base + hdr_bytes + comp_bytes);
-    *d_image = reinterpret_cast<const u32 *>(base + hdr_bytes + comp_bytes + fill_bytes);
+    md.paged = 0, md.pool = nullptr, md.pool_pages = 0, md.pool_next = nullptr, md.pool_overflow = nullptr;
+    out.dense = md;
+    md.comps = reinterpret_cast<const CompDesc *>(base + o_cp);
+    md.ws_bytes = m.ws_bytes_paged;
+    md.paged = 1;
+    out.paged = md;
+    out.fills_dense = reinterpret_cast<const FillRegion *>(base + o_fd);
+    out.fills_paged = reinterpret_cast<const FillRegion *>(base + o_fp);
+    out.n_fills_dense = int(m.fills.size()), out.n_fills_paged = int(m.fills_paged.size());
+    out.image = reinterpret_cast<const u32 *>(base + o_im);
     return ZPAQGPU_OK;
 }
 
-// How many blocks can have their tables resident at once.
-int plan_slots(zpaqgpu_ctx *ctx, const Model &m, int n_blocks, size_t other_bytes, int *slots) {
+// Where the model tables of a batch live: dense slots (one wave = as many blocks as fit) or, for
+// chain-shaped models whose dense tables do not fit, page tables plus a shared page pool.
+struct TablePlan {
+    bool paged = false;
+    int slots = 0;        // blocks per wave
+    u64 stride = 0;       // workspace bytes per block
+    u64 pool_bytes = 0;
+};
+
+int plan_tables(zpaqgpu_ctx *ctx, const Model &m, int n_blocks, size_t other_bytes, bool chain, bool force_dense,
+                TablePlan &tp) {
     size_t free_b = 0, total_b = 0;
     CK(cudaMemGetInfo(&free_b, &total_b));
-    free_b += ctx->workspace.cap;  // our own cached workspace can be reused
+    free_b += ctx->workspace.cap + ctx->pool.cap;  // our own cached buffers can be reused
     u64 budget = ctx->ws_limit ? ctx->ws_limit : u64(double(free_b) * 0.80);
     if (!ctx->ws_limit && budget > other_bytes) budget -= std::min<u64>(other_bytes, budget / 2);
-    u64 n = m.ws_bytes ? budget / m.ws_bytes : u64(n_blocks);
-    if (n < 1) {
+    const u64 dense_slots = m.ws_bytes ? budget / m.ws_bytes : u64(n_blocks);
+    const bool can_page = chain && m.ws_bytes_paged > 0 && !force_dense && ctx->table_mode != ZPAQGPU_TABLES_DENSE;
+    const bool want_page = can_page && (ctx->table_mode == ZPAQGPU_TABLES_PAGED || dense_slots < u64(n_blocks));
+    if (want_page) {
+        u64 ht_bytes = 0;
+        for (const CompDesc &c : m.comps)
+            if (c.type == C_ICM || c.type == C_ISSE) ht_bytes += c.ht_len;
+        const u64 max_blocks = (budget / 2) / m.ws_bytes_paged;  // at most half the budget for page tables
+        if (max_blocks >= 1) {
+            const u64 slots = std::min<u64>(max_blocks, u64(n_blocks));
+            u64 pool = std::min<u64>(budget - slots * m.ws_bytes_paged, slots * ht_bytes);
+            pool = pool / kPageBytes * kPageBytes;
+            if (pool / kPageBytes > 0xFFFFFFF0ull) pool = 0xFFFFFFF0ull * kPageBytes;
+            if (pool >= kPageBytes * 16) {
+                tp.paged = true, tp.slots = int(slots), tp.stride = m.ws_bytes_paged, tp.pool_bytes = pool;
+                return ZPAQGPU_OK;
+            }
+        }
+    }
+    if (dense_slots < 1) {
         ctx->err = "model tables (" + std::to_string(m.ws_bytes) + " bytes per block) exceed the workspace budget";
         return ZPAQGPU_E_NOMEM;
     }
-    *slots = int(std::min<u64>(n, u64(n_blocks)));
+    tp.paged = false, tp.slots = int(std::min<u64>(dense_slots, u64(n_blocks))), tp.stride = m.ws_bytes, tp.pool_bytes = 0;
+    return ZPAQGPU_OK;
+}
+
+// Clear and initialise the tables of one wave; returns the ModelDev to launch with.
+int prepare_wave(zpaqgpu_ctx *ctx, const ModelOnDev &mod, const TablePlan &tp, int n, ModelDev &md) {
+    cudaStream_t st = ctx->stream;
+    CK(cudaMemsetAsync(ctx->workspace.p, 0, u64(n) * tp.stride, st));
+    FillArgs fa{static_cast<u8 *>(ctx->workspace.p), tp.stride, n,
+                tp.paged ? mod.fills_paged : mod.fills_dense, tp.paged ? mod.n_fills_paged : mod.n_fills_dense,
+                mod.image};
+    launch_fill(fa, st);
+    md = tp.paged ? mod.paged : mod.dense;
+    if (tp.paged) {
+        CK(cudaMemsetAsync(ctx->pool.p, 0, tp.pool_bytes, st));
+        CK(cudaMemsetAsync(static_cast<u8 *>(ctx->misc.p) + 16, 0, 8, st));
+        md.pool = static_cast<u8 *>(ctx->pool.p);
+        md.pool_pages = u32(tp.pool_bytes / kPageBytes);
+        md.pool_next = reinterpret_cast<u32 *>(static_cast<u8 *>(ctx->misc.p) + 16);
+        md.pool_overflow = md.pool_next + 1;
+    }
+    return ZPAQGPU_OK;
+}
+
+// After a paged wave: pages used, and whether the pool ran dry.
+int wave_pool_status(zpaqgpu_ctx *ctx, u32 &used, bool &overflow) {
+    u32 two[2] = {0, 0};
+    CK(cudaMemcpyAsync(two, static_cast<u8 *>(ctx->misc.p) + 16, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    used = two[0], overflow = two[1] != 0;
     return ZPAQGPU_OK;
 }
 
@@ -279,49 +356,67 @@ int run_compress(zpaqgpu_ctx *ctx, CompressJob &job) {
 
         float init_ms = 0, codec_ms = 0;
         if (!store) {
-            ModelDev md;
-            const FillRegion *d_fills;
-            const u32 *d_image;
-            if ((rc = upload_model(ctx, m, md, &d_fills, &d_image))) return rc;
-            int slots = 0;
-            if ((rc = plan_slots(ctx, m, n_blocks, arena_bytes, &slots))) return rc;
-            if ((rc = ensure(ctx, ctx->workspace, u64(slots) * m.ws_bytes))) return rc;
-            // encoder: three warps per block, as many blocks per CTA as spreads the wave over all SMs
-            int wpc = 4;
-            if (chain) {
-                const int per_sm = (slots + ctx->sm_count - 1) / ctx->sm_count;
-                wpc = std::max(1, std::min(encpipe_max_blocks_per_cta(m), per_sm));
-            }
-            ctx->stats.warps_per_cta = chain ? wpc * 3 : wpc;
-            for (int first = 0; first < n_blocks; first += slots) {
-                const int n = std::min(slots, n_blocks - first);
-                CK(cudaEventRecord(ctx->ev[0], st));
-                CK(cudaMemsetAsync(ctx->workspace.p, 0, u64(n) * m.ws_bytes, st));
-                FillArgs fa{static_cast<u8 *>(ctx->workspace.p), m.ws_bytes, n, d_fills, int(m.fills.size()), d_image};
-                launch_fill(fa, st);
-                CK(cudaEventRecord(ctx->ev[1], st));
-                EncodeArgs ea;
-                ea.model = md, ea.tables = ctx->tables;
-                ea.workspace = static_cast<u8 *>(ctx->workspace.p);
-                ea.in = job.d_in, ea.arena = static_cast<u8 *>(ctx->arena.p);
-                ea.blocks = d_blocks, ea.segs = d_esegs, ea.pay_len = static_cast<u64 *>(ctx->pay_len.p);
-                ea.first_block = first, ea.n_blocks = n;
+            ModelOnDev mod;
+            if ((rc = upload_model(ctx, m, mod))) return rc;
+            if ((rc = ensure(ctx, ctx->misc, 64))) return rc;
+            bool force_dense = false;
+            for (int table_try = 0; table_try < 2; ++table_try) {
+                TablePlan tp;
+                if ((rc = plan_tables(ctx, m, n_blocks, arena_bytes, chain, force_dense, tp))) return rc;
+                if ((rc = ensure(ctx, ctx->workspace, u64(tp.slots) * tp.stride))) return rc;
+                if (tp.paged && (rc = ensure(ctx, ctx->pool, tp.pool_bytes))) return rc;
+                // encoder: three warps per block, as many blocks per CTA as spreads the wave over all SMs
+                int wpc = 4;
                 if (chain) {
-                    if (!launch_encode_pipe3(m, ea, wpc, st)) {
-                        ctx->err = "no chain kernel instantiation for this model";
-                        return ZPAQGPU_E_UNSUPPORTED;
-                    }
-                } else {
-                    k_encode_generic<<<(n + 3) / 4, 128, 0, st>>>(ea);
+                    const int per_sm = (tp.slots + ctx->sm_count - 1) / ctx->sm_count;
+                    wpc = std::max(1, std::min(encpipe_max_blocks_per_cta(m), per_sm));
                 }
-                CK(cudaGetLastError());
-                CK(cudaEventRecord(ctx->ev[2], st));
-                CK(cudaEventSynchronize(ctx->ev[2]));
-                init_ms += elapsed(ctx->ev[0], ctx->ev[1]);
-                codec_ms += elapsed(ctx->ev[1], ctx->ev[2]);
-                ctx->stats.launches += 2 + (m.fills.empty() ? 0 : 1);
-                ctx->stats.codec_launches += 1;
-                ctx->stats.waves += 1;
+                ctx->stats.warps_per_cta = chain ? wpc * 3 : wpc;
+                ctx->stats.paged = tp.paged ? 1 : 0;
+                ctx->stats.workspace_bytes_per_block = tp.stride;
+                bool overflow = false;
+                for (int first = 0; first < n_blocks && !overflow; first += tp.slots) {
+                    const int n = std::min(tp.slots, n_blocks - first);
+                    CK(cudaEventRecord(ctx->ev[0], st));
+                    ModelDev md;
+                    if ((rc = prepare_wave(ctx, mod, tp, n, md))) return rc;
+                    CK(cudaEventRecord(ctx->ev[1], st));
+                    EncodeArgs ea;
+                    ea.model = md, ea.tables = ctx->tables;
+                    ea.workspace = static_cast<u8 *>(ctx->workspace.p);
+                    ea.in = job.d_in, ea.arena = static_cast<u8 *>(ctx->arena.p);
+                    ea.blocks = d_blocks, ea.segs = d_esegs, ea.pay_len = static_cast<u64 *>(ctx->pay_len.p);
+                    ea.first_block = first, ea.n_blocks = n;
+                    if (chain) {
+                        if (!launch_encode_pipe3(m, ea, wpc, st)) {
+                            ctx->err = "no chain kernel instantiation for this model";
+                            return ZPAQGPU_E_UNSUPPORTED;
+                        }
+                    } else {
+                        k_encode_generic<<<(n + 3) / 4, 128, 0, st>>>(ea);
+                    }
+                    CK(cudaGetLastError());
+                    CK(cudaEventRecord(ctx->ev[2], st));
+                    CK(cudaEventSynchronize(ctx->ev[2]));
+                    init_ms += elapsed(ctx->ev[0], ctx->ev[1]);
+                    codec_ms += elapsed(ctx->ev[1], ctx->ev[2]);
+                    ctx->stats.launches += 2 + (m.fills.empty() ? 0 : 1) + (tp.paged ? 2 : 0);
+                    ctx->stats.codec_launches += 1;
+                    ctx->stats.waves += 1;
+                    if (tp.paged) {
+                        u32 used = 0;
+                        if ((rc = wave_pool_status(ctx, used, overflow))) return rc;
+                        ctx->stats.pool_bytes_used = std::max<u64>(ctx->stats.pool_bytes_used, u64(used) * kPageBytes);
+                    }
+                }
+                if (!overflow) break;
+                // the page pool ran dry (incompressible data touches every line): dense waves instead
+                force_dense = true;
+                ctx->stats.retries += 1;
+                if (table_try == 1) {
+                    ctx->err = "page pool overflow with dense tables";
+                    return ZPAQGPU_E_CUDA;
+                }
             }
         }
         ctx->stats.init_ms += init_ms, ctx->stats.codec_ms += codec_ms;
@@ -454,6 +549,8 @@ int run_decompress(zpaqgpu_ctx *ctx, DecompressJob &job, bool caller_owns_plain)
     const int n = int(job.cand.size());
     ctx->stats = zpaqgpu_stats{};
     int rc;
+    bool dense_only = false;       // set after a paged attempt ran out of pool pages
+    bool pool_overflowed = false;
     for (int attempt = 0; attempt < 2; ++attempt) {
         // plaintext slots, back to back in candidate order
         u64 plain_bytes = 0;
@@ -482,10 +579,8 @@ int run_decompress(zpaqgpu_ctx *ctx, DecompressJob &job, bool caller_owns_plain)
             for (size_t g = 0; g < job.models.size(); ++g) {
                 const Model &m = job.models[g];
                 ctx->stats.workspace_bytes_per_block = m.ws_bytes;
-                ModelDev md;
-                const FillRegion *d_fills;
-                const u32 *d_image;
-                if ((rc = upload_model(ctx, m, md, &d_fills, &d_image))) return rc;
+                ModelOnDev mod;
+                if ((rc = upload_model(ctx, m, mod))) return rc;
                 const bool store = m.n == 0;
                 const bool chain = !store && use_chain(ctx, m);
                 if (!store && ctx->kernel_pref == ZPAQGPU_KERNEL_CHAIN && !m.is_chain) {
@@ -499,56 +594,72 @@ int run_decompress(zpaqgpu_ctx *ctx, DecompressJob &job, bool caller_owns_plain)
                     int j = i;
                     while (j < n && job.cand[size_t(j)].group == int(g)) ++j;
                     const int run = j - i;
-                    int slots = run;
-                    if (!store) {
-                        if ((rc = plan_slots(ctx, m, run, plain_bytes, &slots))) return rc;
-                        if ((rc = ensure(ctx, ctx->workspace, u64(slots) * m.ws_bytes))) return rc;
-                    }
-                    const int wpc = chain ? pick_warps_per_cta(ctx, m, slots) : 4;
-                    ctx->stats.warps_per_cta = wpc;
-                    for (int first = i; first < j; first += slots) {
-                        const int cnt = std::min(slots, j - first);
-                        DecodeArgs da;
-                        da.model = md, da.tables = ctx->tables;
-                        da.workspace = static_cast<u8 *>(ctx->workspace.p);
-                        da.arc = job.d_arc, da.arc_len = job.arc_len, da.out = job.d_plain;
-                        da.blocks = static_cast<const DecBlock *>(ctx->desc.p);
-                        da.results = static_cast<DecBlockOut *>(ctx->results.p);
-                        da.seg_recs = static_cast<DecSegRec *>(ctx->seg_recs.p);
-                        da.seg_count = static_cast<u32 *>(ctx->misc.p);
-                        da.seg_cap = seg_cap, da.first_block = first, da.n_blocks = cnt;
-                        CK(cudaEventRecord(ctx->ev[0], st));
-                        if (store) {
-                            CK(cudaEventRecord(ctx->ev[1], st));
-                            launch_decode_store(da, st);
-                        } else {
-                            CK(cudaMemsetAsync(ctx->workspace.p, 0, u64(cnt) * m.ws_bytes, st));
-                            FillArgs fa{static_cast<u8 *>(ctx->workspace.p), m.ws_bytes, cnt, d_fills,
-                                        int(m.fills.size()), d_image};
-                            launch_fill(fa, st);
-                            CK(cudaEventRecord(ctx->ev[1], st));
-                            if (chain) {
-                                if (!launch_decode_chain(m, da, wpc, st)) {
-                                    ctx->err = "no chain kernel instantiation for this model";
-                                    return ZPAQGPU_E_UNSUPPORTED;
-                                }
-                            } else {
-                                k_decode_generic<<<(cnt + 3) / 4, 128, 0, st>>>(da);
-                            }
-                            ctx->stats.launches += 1 + (m.fills.empty() ? 0 : 1);
+                    for (int once = 0; once < 1; ++once) {
+                        TablePlan tp;
+                        tp.slots = run;
+                        if (!store) {
+                            if ((rc = plan_tables(ctx, m, run, plain_bytes, chain, dense_only, tp))) return rc;
+                            if ((rc = ensure(ctx, ctx->workspace, u64(tp.slots) * tp.stride))) return rc;
+                            if (tp.paged && (rc = ensure(ctx, ctx->pool, tp.pool_bytes))) return rc;
+                            ctx->stats.paged = tp.paged ? 1 : 0;
+                            ctx->stats.workspace_bytes_per_block = tp.stride;
                         }
-                        CK(cudaGetLastError());
-                        CK(cudaEventRecord(ctx->ev[2], st));
-                        CK(cudaEventSynchronize(ctx->ev[2]));
-                        ctx->stats.init_ms += elapsed(ctx->ev[0], ctx->ev[1]);
-                        ctx->stats.codec_ms += elapsed(ctx->ev[1], ctx->ev[2]);
-                        ctx->stats.launches += 1;
-                        ctx->stats.codec_launches += 1;
-                        ctx->stats.waves += 1;
+                        const int wpc = chain ? pick_warps_per_cta(ctx, m, tp.slots) : 4;
+                        ctx->stats.warps_per_cta = wpc;
+                        bool overflow = false;
+                        for (int first = i; first < j && !overflow; first += tp.slots) {
+                            const int cnt = std::min(tp.slots, j - first);
+                            DecodeArgs da;
+                            da.tables = ctx->tables;
+                            da.workspace = static_cast<u8 *>(ctx->workspace.p);
+                            da.arc = job.d_arc, da.arc_len = job.arc_len, da.out = job.d_plain;
+                            da.blocks = static_cast<const DecBlock *>(ctx->desc.p);
+                            da.results = static_cast<DecBlockOut *>(ctx->results.p);
+                            da.seg_recs = static_cast<DecSegRec *>(ctx->seg_recs.p);
+                            da.seg_count = static_cast<u32 *>(ctx->misc.p);
+                            da.seg_cap = seg_cap, da.first_block = first, da.n_blocks = cnt;
+                            CK(cudaEventRecord(ctx->ev[0], st));
+                            if (store) {
+                                da.model = mod.dense;
+                                CK(cudaEventRecord(ctx->ev[1], st));
+                                launch_decode_store(da, st);
+                            } else {
+                                if ((rc = prepare_wave(ctx, mod, tp, cnt, da.model))) return rc;
+                                CK(cudaEventRecord(ctx->ev[1], st));
+                                if (chain) {
+                                    if (!launch_decode_chain(m, da, wpc, st)) {
+                                        ctx->err = "no chain kernel instantiation for this model";
+                                        return ZPAQGPU_E_UNSUPPORTED;
+                                    }
+                                } else {
+                                    k_decode_generic<<<(cnt + 3) / 4, 128, 0, st>>>(da);
+                                }
+                                ctx->stats.launches += 1 + (m.fills.empty() ? 0 : 1) + (tp.paged ? 2 : 0);
+                            }
+                            CK(cudaGetLastError());
+                            CK(cudaEventRecord(ctx->ev[2], st));
+                            CK(cudaEventSynchronize(ctx->ev[2]));
+                            ctx->stats.init_ms += elapsed(ctx->ev[0], ctx->ev[1]);
+                            ctx->stats.codec_ms += elapsed(ctx->ev[1], ctx->ev[2]);
+                            ctx->stats.launches += 1;
+                            ctx->stats.codec_launches += 1;
+                            ctx->stats.waves += 1;
+                            if (!store && tp.paged) {
+                                u32 used = 0;
+                                if ((rc = wave_pool_status(ctx, used, overflow))) return rc;
+                                ctx->stats.pool_bytes_used =
+                                    std::max<u64>(ctx->stats.pool_bytes_used, u64(used) * kPageBytes);
+                            }
+                        }
+                        if (overflow) pool_overflowed = true;
+                        break;
                     }
+                    if (pool_overflowed) break;
                     i = j;
                 }
+                if (pool_overflowed) break;
             }
+            if (pool_overflowed) break;
             // results
             if ((rc = ensure_pinned(ctx, sizeof(DecBlockOut) * size_t(n) + 64))) return rc;
             u32 *h_count = static_cast<u32 *>(ctx->pinned);
@@ -568,6 +679,18 @@ int run_decompress(zpaqgpu_ctx *ctx, DecompressJob &job, bool caller_owns_plain)
                 CK(cudaMemcpy(job.recs.data(), ctx->seg_recs.p, sizeof(DecSegRec) * size_t(count), cudaMemcpyDeviceToHost));
             }
             break;
+        }
+        if (pool_overflowed) {
+            // incompressible data touched more lines than the page pool holds: the whole call is
+            // repeated with dense tables in as many waves as needed
+            if (dense_only) {
+                ctx->err = "page pool overflow with dense tables";
+                return ZPAQGPU_E_CUDA;
+            }
+            dense_only = true, pool_overflowed = false;
+            ctx->stats.retries += 1;
+            --attempt;
+            continue;
         }
         bool overflow = false;
         for (int i = 0; i < n; ++i) {
@@ -722,7 +845,7 @@ void zpaqgpu_destroy(zpaqgpu_ctx *ctx) {
     if (ctx->own_stream) cudaStreamSynchronize(ctx->own_stream);
     DevBuf *bufs[] = {&ctx->workspace, &ctx->in, &ctx->arena, &ctx->out, &ctx->desc, &ctx->pay_len,
                       &ctx->digests, &ctx->seg_size, &ctx->out_off, &ctx->modelblob, &ctx->results,
-                      &ctx->seg_recs, &ctx->misc, &ctx->heads, &ctx->plain};
+                      &ctx->seg_recs, &ctx->misc, &ctx->heads, &ctx->plain, &ctx->pool};
     for (DevBuf *b : bufs)
         if (b->p) cudaFree(b->p);
     if (ctx->tables_mem) cudaFree(ctx->tables_mem);
@@ -741,6 +864,11 @@ const char *zpaqgpu_last_error(const zpaqgpu_ctx *ctx) { return ctx ? ctx->err.c
 int zpaqgpu_set_kernel(zpaqgpu_ctx *ctx, int kernel) {
     if (!ctx || kernel < 0 || kernel > 2) return ZPAQGPU_E_ARG;
     ctx->kernel_pref = kernel;
+    return ZPAQGPU_OK;
+}
+int zpaqgpu_set_table_mode(zpaqgpu_ctx *ctx, int mode) {
+    if (!ctx || mode < 0 || mode > 2) return ZPAQGPU_E_ARG;
+    ctx->table_mode = mode;
     return ZPAQGPU_OK;
 }
 int zpaqgpu_set_workspace_limit(zpaqgpu_ctx *ctx, uint64_t bytes) {

@@ -37,7 +37,32 @@ struct ModelDev {
     const CompDesc *comps;
     // chain-kernel shape
     i32 ctx_mode, n_hash;
+    // paged hash tables (chain kernels): comps[].ht_off is then the block's page table (one u32 per
+    // kPageBytes of virtual table, 0 = not mapped) and pages come from a pool shared by the wave
+    i32 paged;
+    u32 pool_pages;
+    u8 *pool;
+    u32 *pool_next;      // bump allocator
+    u32 *pool_overflow;  // set when the pool ran dry: the host repeats the wave with dense tables
 };
+
+// Address of the 16-byte slot at virtual offset h0 of a hash table (dense: base + h0; paged: through
+// the page table, mapping a zero page on first touch).  Only the owning lane touches its table.
+__device__ __forceinline__ u8 *ht_slot(const ModelDev &M, u8 *ht, u32 h0) {
+    if (!M.paged) return ht + h0;
+    u32 *pt = reinterpret_cast<u32 *>(ht);
+    const u32 pg = h0 / kPageBytes;
+    u32 pte = pt[pg];
+    if (pte == 0) {
+        pte = atomicAdd(M.pool_next, 1u) + 1u;
+        if (pte > M.pool_pages) {
+            *M.pool_overflow = 1u;
+            pte = 1u;  // stay in bounds; the result of this wave is discarded
+        }
+        pt[pg] = pte;
+    }
+    return M.pool + u64(pte - 1u) * kPageBytes + (h0 & (kPageBytes - 1u));
+}
 
 // ---- compression work descriptors ----
 struct EncSeg {

@@ -29,7 +29,6 @@ namespace {
 
 constexpr int kRing = 256;       // input ring (bytes), power of two
 constexpr int kOutStage = 256;   // decoder plaintext stage (bytes)
-constexpr u32 kNoSlot = 0xFFFFFFFFu;
 constexpr unsigned kFull = 0xFFFFFFFFu;
 
 __host__ __device__ constexpr size_t warp_smem_bytes(int ni, bool mix2) {
@@ -58,11 +57,12 @@ struct Chain {
     u8 *ring;
     u8 *stage;
     // per lane: the hash table of component `lane`, its parked slot and context hash
-    u8 *ht;
+    u8 *ht;            // hash table (dense) or its page table (paged)
     u32 ht_len;
     int sizebits;
-    u32 slot_at;
+    u8 *slot_at;       // where the parked slot lives in HBM (nullptr: none yet)
     uint4 sl;
+    const ModelDev *md;
     u32 h;
     bool owner;        // lane <= NI
     // MIX2
@@ -104,7 +104,8 @@ struct Chain {
             const CompDesc &cd = M.comps[lane];
             ht = ws + cd.ht_off, ht_len = cd.ht_len, sizebits = cd.a + 2;
         }
-        slot_at = kNoSlot;
+        slot_at = nullptr;
+        md = &M;
         sl = make_uint4(0, 0, 0, 0);
         h = 0, hist = 0, mix_h = 0;
         a16 = nullptr, a16_mask = 0, mix_sel = 0, mix_rate = 0;
@@ -170,19 +171,23 @@ struct Chain {
     // nibble goes back to its table first (the reference updates the table in place).
     __device__ __forceinline__ void probe(u32 c8v) {
         if (owner) {
-            if (slot_at != kNoSlot) *reinterpret_cast<uint4 *>(ht + slot_at) = sl;
+            if (slot_at) *reinterpret_cast<uint4 *>(slot_at) = sl;
             const u32 key = h + 16u * c8v;
             const u32 chk = (key >> sizebits) & 255u;
-            const u32 h0 = (key * 16u) & (ht_len - 16u), h1 = h0 ^ 16u, h2 = h0 ^ 32u;
+            const u32 h0 = (key * 16u) & (ht_len - 16u);
+            // the three candidates h0, h0^16, h0^32 share one 64-byte line (and one page)
+            u8 *b0 = ht_slot(*md, ht, h0);
+            u8 *b1 = reinterpret_cast<u8 *>(reinterpret_cast<uintptr_t>(b0) ^ 16u);
+            u8 *b2 = reinterpret_cast<u8 *>(reinterpret_cast<uintptr_t>(b0) ^ 32u);
             // All three candidates are requested before any is looked at and the choice is made
             // with selects: written as an if-chain the compiler makes the second and third load
             // conditional, which serialises three HBM round trips.
-            const uint4 s0 = ldg128(ht + h0), s1 = ldg128(ht + h1), s2 = ldg128(ht + h2);
+            const uint4 s0 = ldg128(b0), s1 = ldg128(b1), s2 = ldg128(b2);
             const bool m0 = (s0.x & 255u) == chk, m1 = (s1.x & 255u) == chk, m2 = (s2.x & 255u) == chk;
             const u32 q0 = (s0.x >> 8) & 255u, q1 = (s1.x >> 8) & 255u, q2 = (s2.x >> 8) & 255u;
-            const u32 victim = (q0 <= q1 && q0 <= q2) ? h0 : (q1 < q2 ? h1 : h2);
+            u8 *victim = (q0 <= q1 && q0 <= q2) ? b0 : (q1 < q2 ? b1 : b2);
             const bool hit = m0 | m1 | m2;
-            slot_at = m0 ? h0 : m1 ? h1 : m2 ? h2 : victim;
+            slot_at = m0 ? b0 : m1 ? b1 : m2 ? b2 : victim;
             uint4 pick = m0 ? s0 : (m1 ? s1 : s2);
             sl.x = hit ? pick.x : chk;
             sl.y = hit ? pick.y : 0u;

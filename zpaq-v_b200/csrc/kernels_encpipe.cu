@@ -38,7 +38,6 @@ constexpr int kTick = 32;     // nibbles per barrier interval
 constexpr int kDepth = 128;   // ring depth in nibbles
 constexpr int kInRing = 512;  // plaintext ring, bytes
 constexpr int kStage = 512;   // coder output stage, bytes
-constexpr u32 kNone = 0xFFFFFFFFu;
 constexpr unsigned kAll = 0xFFFFFFFFu;
 constexpr size_t kTables = 32768 * 2 + 4096 * 2 + 512;
 
@@ -142,8 +141,8 @@ __global__ void __launch_bounds__(672, 1) k_encode_pipe3(EncodeArgs A, int block
     // role-private state that lives across segments (tables and ZPAQL memory persist, Q17)
     Ctx cx{M.ctx_mode, M.n_hash, M.n, 0u};
     // H
-    u8 *ht = nullptr;
-    u32 ht_len = 16, slot_at = kNone;
+    u8 *ht = nullptr, *slot_at = nullptr;
+    u32 ht_len = 16;
     int sizebits = 0;
     uint4 sl = make_uint4(0, 0, 0, 0);
     // C
@@ -218,7 +217,7 @@ __global__ void __launch_bounds__(672, 1) k_encode_pipe3(EncodeArgs A, int block
                         c = vbyte(vb);
                         // the two lines byte vb+2 will touch are already determined: pull them into L2
                         // (two bytes of lead cover an HBM round trip even when this warp runs alone)
-                        if (owner && vb + 2 < total) {
+                        if (owner && !M.paged && vb + 2 < total) {
                             u32 nh1, nh2;
                             (void)cx.next(c, lane, nh1);
                             Ctx ahead = cx;
@@ -235,16 +234,19 @@ __global__ void __launch_bounds__(672, 1) k_encode_pipe3(EncodeArgs A, int block
                     if (owner) {
                         // Predictor.find_ht (predictor.v:495-532); the slot of the previous nibble goes
                         // back first (the reference updates the table in place)
-                        if (slot_at != kNone) *reinterpret_cast<uint4 *>(ht + slot_at) = sl;
+                        if (slot_at) *reinterpret_cast<uint4 *>(slot_at) = sl;
                         const u32 key = h + 16u * c8;
                         const u32 chk = (key >> sizebits) & 255u;
-                        const u32 h0 = (key * 16u) & (ht_len - 16u), h1 = h0 ^ 16u, h2 = h0 ^ 32u;
-                        const uint4 a0 = ld128(ht + h0), a1 = ld128(ht + h1), a2 = ld128(ht + h2);
+                        const u32 h0 = (key * 16u) & (ht_len - 16u);
+                        u8 *b0 = ht_slot(M, ht, h0);
+                        u8 *b1 = reinterpret_cast<u8 *>(reinterpret_cast<uintptr_t>(b0) ^ 16u);
+                        u8 *b2 = reinterpret_cast<u8 *>(reinterpret_cast<uintptr_t>(b0) ^ 32u);
+                        const uint4 a0 = ld128(b0), a1 = ld128(b1), a2 = ld128(b2);
                         const bool m0 = (a0.x & 255u) == chk, m1 = (a1.x & 255u) == chk, m2 = (a2.x & 255u) == chk;
                         const u32 q0 = (a0.x >> 8) & 255u, q1 = (a1.x >> 8) & 255u, q2 = (a2.x >> 8) & 255u;
-                        const u32 victim = (q0 <= q1 && q0 <= q2) ? h0 : (q1 < q2 ? h1 : h2);
+                        u8 *victim = (q0 <= q1 && q0 <= q2) ? b0 : (q1 < q2 ? b1 : b2);
                         const bool hit = m0 | m1 | m2;
-                        slot_at = m0 ? h0 : m1 ? h1 : m2 ? h2 : victim;
+                        slot_at = m0 ? b0 : m1 ? b1 : m2 ? b2 : victim;
                         const uint4 pick = m0 ? a0 : (m1 ? a1 : a2);
                         sl.x = hit ? pick.x : chk, sl.y = hit ? pick.y : 0u;
                         sl.z = hit ? pick.z : 0u, sl.w = hit ? pick.w : 0u;

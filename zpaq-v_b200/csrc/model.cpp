@@ -1,6 +1,7 @@
 // model.cpp -- header parsing, workspace layout, constant tables (host side of libzpaqgpu).
 #include "model.h"
 
+#include <algorithm>
 #include <cstring>
 #include <mutex>
 
@@ -216,13 +217,19 @@ uint32_t add_image(Model &m, const std::vector<uint32_t> &img) {
     return at;
 }
 
-int build_components(Model &m) {
+int build_layout(Model &m, bool paged) {
     const std::vector<uint8_t> &hd = m.header;
     const int len = int(hd.size());
-    m.comps.clear();
-    m.fills.clear();
-    m.image.clear();
+    std::vector<CompDesc> &comps_out = paged ? m.comps_paged : m.comps;
+    std::vector<FillRegion> &fills_out = paged ? m.fills_paged : m.fills;
+    comps_out.clear();
+    fills_out.clear();
+    if (!paged) m.image.clear();
     m.n = len >= 5 ? hd[4] : 0;
+    // a hash table of `bytes` occupies its page table in the paged layout
+    auto ht_resident = [&](uint64_t bytes) {
+        return paged ? std::max<uint64_t>(4, bytes / kPageBytes * 4) : bytes;
+    };
     uint64_t ws = 0;
     auto reserve = [&](uint64_t bytes) {
         ws = align_up(ws, 256);
@@ -230,10 +237,10 @@ int build_components(Model &m) {
         ws += bytes;
         return at;
     };
-    m.comps.assign(size_t(m.n), CompDesc{});
+    comps_out.assign(size_t(m.n), CompDesc{});
     int cp = 5;
     for (int i = 0; i < m.n && cp < m.cend; ++i) {
-        CompDesc &c = m.comps[size_t(i)];
+        CompDesc &c = comps_out[size_t(i)];
         const int type = hd[size_t(cp)];
         c.type = type;
         const int need = (type >= 0 && type < 10) ? kCompSize[type] : 1;
@@ -253,7 +260,7 @@ int build_components(Model &m) {
             if (c.a > 26) return m.error = "CM sizebits > 26", ZPAQGPU_E_UNSUPPORTED;
             c.cm_len = 1u << c.a;
             c.cm_off = reserve(uint64_t(c.cm_len) * 4);
-            m.fills.push_back({c.cm_off, c.cm_len, add_image(m, {0x80000000u}), 1});
+            fills_out.push_back({c.cm_off, c.cm_len, add_image(m, {0x80000000u}), 1});
             cp += 3;
             break;
         }
@@ -263,10 +270,10 @@ int build_components(Model &m) {
             c.cm_len = 256;
             c.cm_off = reserve(256 * 4);
             c.ht_len = 16u << (c.a + 2);
-            c.ht_off = reserve(c.ht_len);
+            c.ht_off = reserve(ht_resident(c.ht_len));
             std::vector<uint32_t> img(256);
             for (int j = 0; j < 256; ++j) img[size_t(j)] = uint32_t(st_cminit(j));
-            m.fills.push_back({c.cm_off, 256, add_image(m, img), 256});
+            fills_out.push_back({c.cm_off, 256, add_image(m, img), 256});
             cp += 2;
             break;
         }
@@ -292,7 +299,7 @@ int build_components(Model &m) {
             c.a16_len = 1u << c.a;
             const uint64_t words = (uint64_t(c.a16_len) * 2 + 3) / 4;
             c.a16_off = reserve(words * 4);
-            m.fills.push_back({c.a16_off, words, add_image(m, {0x80008000u}), 1});
+            fills_out.push_back({c.a16_off, words, add_image(m, {0x80008000u}), 1});
             cp += 6;
             break;
         }
@@ -305,7 +312,7 @@ int build_components(Model &m) {
             c.p[0] = uint32_t(P(4)), c.p[1] = uint32_t(P(5));
             c.cm_len = uint32_t(size) * uint32_t(mm);
             c.cm_off = reserve(uint64_t(c.cm_len) * 4);
-            m.fills.push_back({c.cm_off, c.cm_len, add_image(m, {uint32_t(65536 / mm) << 8}), 1});
+            fills_out.push_back({c.cm_off, c.cm_len, add_image(m, {uint32_t(65536 / mm) << 8}), 1});
             cp += 6;
             break;
         }
@@ -315,13 +322,13 @@ int build_components(Model &m) {
             c.cm_len = 512;
             c.cm_off = reserve(512 * 4);
             c.ht_len = 16u << (c.a + 2);
-            c.ht_off = reserve(c.ht_len);
+            c.ht_off = reserve(ht_resident(c.ht_len));
             std::vector<uint32_t> img(512);
             for (int k = 0; k < 256; ++k) {
                 img[size_t(k) * 2] = 1u << 15;
                 img[size_t(k) * 2 + 1] = uint32_t(h_clamp512k(h_stretch(st_cminit(k) >> 8) * 1024));
             }
-            m.fills.push_back({c.cm_off, 512, add_image(m, img), 512});
+            fills_out.push_back({c.cm_off, 512, add_image(m, img), 512});
             cp += 3;
             break;
         }
@@ -334,7 +341,7 @@ int build_components(Model &m) {
             c.cm_off = reserve(uint64_t(c.cm_len) * 4);
             std::vector<uint32_t> img(32);
             for (int k = 0; k < 32; ++k) img[size_t(k)] = (uint32_t(h_squash(k * 64 - 992)) << 17) | uint32_t(start);
-            m.fills.push_back({c.cm_off, c.cm_len, add_image(m, img), 32});
+            fills_out.push_back({c.cm_off, c.cm_len, add_image(m, img), 32});
             cp += 5;
             break;
         }
@@ -346,6 +353,10 @@ int build_components(Model &m) {
     // ZPAQL memory (zpaql.v:74-96): allocated only for 0 < bits < 32
     const int hh = len >= 2 ? hd[0] : 0, hm = len >= 2 ? hd[1] : 0;
     if (hh > 26 || hm > 30) return m.error = "H/M array too large", ZPAQGPU_E_UNSUPPORTED;
+    if (paged) {  // chain kernels evaluate HCOMP in closed form: no ZPAQL memory in this layout
+        m.ws_bytes_paged = align_up(ws, 256);
+        return ZPAQGPU_OK;
+    }
     m.h_len = hh > 0 ? 1u << hh : 0;
     m.m_len = hm > 0 ? 1u << hm : 0;
     m.h_off = reserve(uint64_t(m.h_len) * 4);
@@ -438,9 +449,10 @@ int model_from_level_layout(const uint8_t *hdr, int len, Model &m) {
     } else {
         m.cend = m.hbegin = m.hend = len;
     }
-    const int rc = build_components(m);
+    const int rc = build_layout(m, false);
     if (rc != ZPAQGPU_OK) return rc;
     detect_shape(m);
+    if (m.is_chain) build_layout(m, true);
     build_block_prefix(m);
     return ZPAQGPU_OK;
 }
@@ -484,9 +496,10 @@ int model_from_archive(const uint8_t *p, uint64_t avail, Model &m, uint64_t *con
     }
     m.hend = int(h.size()) - 1;
     if (consumed) *consumed = at;
-    const int rc = build_components(m);
+    const int rc = build_layout(m, false);
     if (rc != ZPAQGPU_OK) return rc;
     detect_shape(m);
+    if (m.is_chain) build_layout(m, true);
     return ZPAQGPU_OK;
 }
 

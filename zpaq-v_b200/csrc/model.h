@@ -27,6 +27,8 @@ struct CompDesc {
     uint32_t a16_len;
 };
 
+constexpr uint32_t kPageBytes = 256;   // 4 hash lines of 64 bytes
+
 struct FillRegion {              // workspace words that do not start as zero
     uint64_t off;                // byte offset inside the block workspace (4-aligned)
     uint64_t n_words;
@@ -47,6 +49,11 @@ struct Model {
     uint32_t h_len = 0, m_len = 0;
     uint64_t ws_bytes = 0;       // workspace stride per block
     std::vector<FillRegion> fills;
+    // Paged layout (chain-shaped models only): the ICM/ISSE hash tables are virtual; per block only a
+    // page table (one u32 per 256-byte page) is resident and pages come from a pool shared by the wave.
+    std::vector<CompDesc> comps_paged;   // ht_off = offset of the page table, ht_len = virtual length
+    std::vector<FillRegion> fills_paged;
+    uint64_t ws_bytes_paged = 0;
     std::vector<uint32_t> image;
     // bytes start_block writes: locator "zPQ" lvl 1 hsize COMP HCOMP (compressor.v:150-181)
     std::vector<uint8_t> block_prefix;
