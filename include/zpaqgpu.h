@@ -162,6 +162,60 @@ int zpaqgpu_segment_end(zpaqgpu_ctx *ctx);
  * or ZPAQGPU_E_NOSPACE with *need set (call again with a larger buffer; the block is kept). */
 int64_t zpaqgpu_block_end(zpaqgpu_ctx *ctx, uint8_t *out, uint64_t cap, uint64_t *need);
 
+/* ---- jidac front end: fragmentation, fragment hashing, dedup, journaling archive ------------ */
+/* Stands in for JidacArchive.create_archive (jidac.v:181-296) and widens it by what the task's
+ * north star asks of `jidac add`: content-defined fragmentation with a rolling hash and SHA-1
+ * deduplication of fragments, each its own kernel.  The reference always makes ONE fragment per
+ * file, never deduplicates and always stores d blocks (jidac.v:94-118); opts {fragment = -1,
+ * dedup = 0, block_bytes = 0, level = 0} reproduces exactly those bytes.  The fragmentation rule
+ * for fragment >= 0 is upstream zpaq's (order-1 predicted rolling hash, min 64<<fragment, max
+ * 8128<<fragment bytes); its source is not part of the reference, parity there is unpinned. */
+typedef struct {
+    int64_t date;         /* YYYYMMDDHHMMSS as get_jidac_date() makes it (jidac.v:31-35)            */
+    int32_t level;        /* method of the d blocks, 0..5; 0 = store, what the reference always uses */
+    int32_t fragment;     /* -1: one fragment per file; 0..22: rolling-hash cut, average 1024<<fragment;
+                             >22: fixed fragments of 8128<<fragment bytes                           */
+    int32_t dedup;        /* 1: fragments with equal SHA-1 and size are stored once                 */
+    int32_t reserved;
+    uint64_t block_bytes; /* stored fragments are packed into d blocks of up to this many bytes;
+                             0 = one d block per stored fragment (the reference: one per file)      */
+} zpaqgpu_jidac_opts;
+
+typedef struct {
+    uint64_t off, len;    /* byte range inside `in`                                                 */
+    uint32_t file;        /* index of the file the fragment belongs to                              */
+    uint32_t id;          /* 1-based fragment id as the h and i blocks use it (jidac.v:153-163);
+                             duplicates carry the id of their first occurrence                      */
+    uint32_t stored;      /* 1: first occurrence, its bytes go into a d block                       */
+    uint8_t sha1[20];
+} zpaqgpu_fragment;
+
+/* Fragment boundaries, SHA-1 and dedup ids of n_files byte ranges in_off[k]..in_off[k+1] of `in`
+ * (files in archive order).  frags receives up to cap records in file order; *n_frags the count
+ * (ZPAQGPU_E_NOSPACE when cap is too small, *n_frags then holds the required count), *n_stored how
+ * many are first occurrences. */
+int zpaqgpu_jidac_fragment(zpaqgpu_ctx *ctx, const uint8_t *in, const uint64_t *in_off, int n_files,
+                           int fragment, int dedup, zpaqgpu_fragment *frags, int cap, int *n_frags,
+                           int *n_stored);
+
+/* A complete journaling archive of the files: c block, d blocks, one h block per d block, i block
+ * (jidac.v:181-296; block names jDC<date14><type><num10>, comment "<usize> jDC\x01", jidac.v:47-91).
+ * names[k] are NUL-terminated.  ZPAQGPU_E_NOSPACE sets *out_need. */
+int zpaqgpu_jidac_add(zpaqgpu_ctx *ctx, const zpaqgpu_jidac_opts *opts, const char *const *names,
+                      const uint8_t *in, const uint64_t *in_off, int n_files, uint8_t *out,
+                      uint64_t out_cap, uint64_t *out_len, uint64_t *out_need);
+
+typedef struct {
+    float h2d_ms, fragment_ms, sha1_ms, dedup_ms, gather_ms; /* front-end stages            */
+    float codec_ms;        /* d-block codec kernel                                           */
+    float pack_ms, d2h_ms;
+    int32_t launches;      /* kernels launched by the last jidac call                        */
+    int32_t n_files, n_fragments, n_stored, n_dblocks;
+    int32_t reserved;
+    uint64_t input_bytes, stored_bytes, archive_bytes;
+} zpaqgpu_jidac_stats;
+int zpaqgpu_jidac_last_stats(const zpaqgpu_ctx *ctx, zpaqgpu_jidac_stats *out);
+
 /* ---- measurement ------------------------------------------------------------------------ */
 typedef struct {
     float init_ms;     /* table zero/fill kernels                      */

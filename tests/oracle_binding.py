@@ -75,6 +75,14 @@ def lib():
     L.zo_decompresser_comment.restype = C.c_char_p
     L.zo_decompresser_decompress.argtypes = [C.c_void_p, C.c_int]
     L.zo_decompresser_read_segment_end.argtypes = [C.c_void_p]
+    L.zo_fragment.argtypes = [C.c_char_p, C.c_size_t, C.c_int, C.c_void_p, C.c_size_t]
+    L.zo_fragment.restype = C.c_size_t
+    L.zo_jidac_fragment.argtypes = [C.c_char_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_long,
+                                    C.POINTER(C.c_long)]
+    L.zo_jidac_fragment.restype = C.c_long
+    L.zo_jidac_add.argtypes = [C.c_longlong, C.c_int, C.c_int, C.c_int, C.c_uint64, C.c_void_p, C.c_char_p,
+                               C.c_void_p, C.c_int, C.POINTER(u8p)]
+    L.zo_jidac_add.restype = C.c_size_t
     _LIB = L
     return L
 
@@ -226,3 +234,48 @@ class Decompresser:
     def output(self):
         b = lib().zo_decompresser_output(self._h).contents
         return C.string_at(b.data, b.len) if b.len else b""
+
+
+# ---- jidac front end (oracle/jidac_oracle.c) ----
+class _Frag(C.Structure):
+    _fields_ = [("off", C.c_uint64), ("len", C.c_uint64), ("file", C.c_uint32), ("id", C.c_uint32),
+                ("stored", C.c_uint32), ("sha1", C.c_uint8 * 20)]
+
+
+def fragment_ends(data, fragment):
+    data = bytes(data)
+    n = lib().zo_fragment(data, len(data), fragment, None, 0)
+    ends = (C.c_uint64 * max(n, 1))()
+    lib().zo_fragment(data, len(data), fragment, ends, n)
+    return list(ends[:n])
+
+
+def _ranges(files):
+    n = len(files)
+    off = (C.c_uint64 * (n + 1))()
+    pos = 0
+    for i, b in enumerate(files):
+        off[i] = pos
+        pos += len(b)
+    off[n] = pos
+    return n, b"".join(bytes(b) for b in files), off
+
+
+def jidac_fragment(files, fragment, dedup):
+    n, data, off = _ranges(files)
+    ns = C.c_long(0)
+    cnt = lib().zo_jidac_fragment(data, off, n, fragment, int(dedup), None, 0, C.byref(ns))
+    frs = (_Frag * max(cnt, 1))()
+    lib().zo_jidac_fragment(data, off, n, fragment, int(dedup), frs, cnt, C.byref(ns))
+    return [dict(off=f.off, len=f.len, file=f.file, id=f.id, stored=f.stored, sha1=bytes(f.sha1))
+            for f in frs[:cnt]], ns.value
+
+
+def jidac_add(names, files, date, level=0, fragment=-1, dedup=False, block_bytes=0):
+    n, data, off = _ranges(files)
+    arr = (C.c_char_p * max(n, 1))()
+    for i, x in enumerate(names):
+        arr[i] = x.encode() if isinstance(x, str) else x
+    p = C.POINTER(C.c_uint8)()
+    ln = lib().zo_jidac_add(date, level, fragment, int(dedup), block_bytes, arr, data, off, n, C.byref(p))
+    return _take(p, ln)

@@ -21,6 +21,7 @@ EXPORTS = [
     "zpaqgpu_find_blocks", "zpaqgpu_decompress_archive", "zpaqgpu_decompress_blocks_dev",
     "zpaqgpu_block_begin", "zpaqgpu_block_begin_header", "zpaqgpu_segment_begin", "zpaqgpu_segment_write",
     "zpaqgpu_segment_end", "zpaqgpu_block_end", "zpaqgpu_last_stats", "zpaqgpu_describe_model",
+    "zpaqgpu_jidac_fragment", "zpaqgpu_jidac_add", "zpaqgpu_jidac_last_stats",
 ]
 
 
@@ -43,6 +44,28 @@ class Stats(C.Structure):
                 ("codec_launches", C.c_int32), ("waves", C.c_int32), ("retries", C.c_int32), ("kernel", C.c_int32),
                 ("warps_per_cta", C.c_int32), ("workspace_bytes_per_block", C.c_uint64),
                 ("pool_bytes_used", C.c_uint64), ("paged", C.c_int32), ("reserved", C.c_int32)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+class JidacOpts(C.Structure):
+    _fields_ = [("date", C.c_int64), ("level", C.c_int32), ("fragment", C.c_int32), ("dedup", C.c_int32),
+                ("reserved", C.c_int32), ("block_bytes", C.c_uint64)]
+
+
+class Fragment(C.Structure):
+    _fields_ = [("off", C.c_uint64), ("len", C.c_uint64), ("file", C.c_uint32), ("id", C.c_uint32),
+                ("stored", C.c_uint32), ("sha1", C.c_uint8 * 20)]
+
+
+class JidacStats(C.Structure):
+    _fields_ = [("h2d_ms", C.c_float), ("fragment_ms", C.c_float), ("sha1_ms", C.c_float),
+                ("dedup_ms", C.c_float), ("gather_ms", C.c_float), ("codec_ms", C.c_float),
+                ("pack_ms", C.c_float), ("d2h_ms", C.c_float), ("launches", C.c_int32), ("n_files", C.c_int32),
+                ("n_fragments", C.c_int32), ("n_stored", C.c_int32), ("n_dblocks", C.c_int32),
+                ("reserved", C.c_int32), ("input_bytes", C.c_uint64), ("stored_bytes", C.c_uint64),
+                ("archive_bytes", C.c_uint64)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -94,6 +117,9 @@ def lib():
     L.zpaqgpu_block_end.restype = C.c_int64
     L.zpaqgpu_last_stats.argtypes = [vp, C.POINTER(Stats)]
     L.zpaqgpu_describe_model.argtypes = [C.c_char_p, C.c_int, C.POINTER(ModelInfo)]
+    L.zpaqgpu_jidac_fragment.argtypes = [vp, vp, vp, C.c_int, C.c_int, C.c_int, vp, C.c_int, i32p, i32p]
+    L.zpaqgpu_jidac_add.argtypes = [vp, C.POINTER(JidacOpts), vp, vp, vp, C.c_int, vp, C.c_uint64, u64p, u64p]
+    L.zpaqgpu_jidac_last_stats.argtypes = [vp, C.POINTER(JidacStats)]
     _lib = L
     return L
 
@@ -252,6 +278,61 @@ class Context:
                                 block_start=s.block_start, block_end=s.block_end, sha1_ok=s.sha1_ok))
             return out.raw[:need.value], res, status
         raise ZpaqGpuError(E_NOSPACE, "output sizing did not converge")
+
+    # ---- jidac front end ----
+    @staticmethod
+    def _file_ranges(files):
+        n = len(files)
+        data = b"".join(bytes(b) for b in files)
+        off = (C.c_uint64 * (n + 1))()
+        pos = 0
+        for i, b in enumerate(files):
+            off[i] = pos
+            pos += len(b)
+        off[n] = pos
+        src = C.create_string_buffer(data, len(data)) if data else C.create_string_buffer(1)
+        return n, src, off, len(data)
+
+    def jidac_fragment(self, files, fragment=6, dedup=True):
+        """Fragment table of the files (list of bytes): list of dicts off/len/file/id/stored/sha1."""
+        n, src, off, total = self._file_ranges(files)
+        cap = 1024
+        while True:
+            frs = (Fragment * cap)()
+            nf, ns = C.c_int(0), C.c_int(0)
+            rc = lib().zpaqgpu_jidac_fragment(self._h, src, off, n, fragment, int(dedup), frs, cap, C.byref(nf),
+                                              C.byref(ns))
+            if rc == E_NOSPACE:
+                cap = nf.value + 16
+                continue
+            self._check(rc)
+            return [dict(off=f.off, len=f.len, file=f.file, id=f.id, stored=f.stored, sha1=bytes(f.sha1))
+                    for f in frs[:nf.value]], ns.value
+
+    def jidac_add(self, names, files, date, level=0, fragment=-1, dedup=False, block_bytes=0):
+        """A journaling archive (c, d.., h.., i blocks) of the files; see include/zpaqgpu.h."""
+        n, src, off, total = self._file_ranges(files)
+        arr = (C.c_char_p * max(n, 1))()
+        for i, x in enumerate(names):
+            arr[i] = x.encode() if isinstance(x, str) else x
+        opts = JidacOpts(date, level, fragment, int(dedup), 0, block_bytes)
+        cap = total + total // 4 + 4096 * (n + 4)
+        ln, need = C.c_uint64(0), C.c_uint64(0)
+        for _ in range(2):
+            out = C.create_string_buffer(cap)
+            rc = lib().zpaqgpu_jidac_add(self._h, C.byref(opts), arr, src, off, n, out, cap, C.byref(ln),
+                                         C.byref(need))
+            if rc == E_NOSPACE:
+                cap = need.value + 16
+                continue
+            self._check(rc)
+            return out.raw[:ln.value]
+        raise ZpaqGpuError(E_NOSPACE, "output sizing did not converge")
+
+    def jidac_stats(self):
+        s = JidacStats()
+        lib().zpaqgpu_jidac_last_stats(self._h, C.byref(s))
+        return s.as_dict()
 
     # ---- streaming-shaped ----
     def block_begin(self, level=None, header=None):

@@ -7,71 +7,11 @@
 #include <string>
 #include <vector>
 
-#include "../../include/zpaqgpu.h"
-#include "common.cuh"
-#include "kernels.h"
-#include "model.h"
+#include "ctx.h"
 
 using namespace zg;
 
-namespace {
-
-struct DevBuf {
-    void *p = nullptr;
-    size_t cap = 0;
-};
-
-struct PendingSeg {
-    std::string name, comment;
-    std::vector<uint8_t> data;
-    bool called = false;  // compress() was called at least once
-};
-
-struct SegSpec {  // one segment of a compression job
-    const char *name, *comment;
-    u64 in_off, in_len;
-    bool called;
-};
-
-}  // namespace
-
-struct zpaqgpu_ctx {
-    int device = 0;
-    cudaStream_t own_stream = nullptr, stream = nullptr, side_stream = nullptr;
-    cudaEvent_t ev[8] = {};
-    cudaEvent_t ev_side = nullptr, ev_main = nullptr;
-    DevTables tables{};
-    void *tables_mem = nullptr;
-    int kernel_pref = ZPAQGPU_KERNEL_AUTO;
-    int table_mode = ZPAQGPU_TABLES_AUTO;
-    u64 ws_limit = 0;
-    int sm_count = 148;
-    std::string err;
-    zpaqgpu_stats stats{};
-    // grow-only device buffers
-    DevBuf workspace, in, arena, out, desc, pay_len, digests, seg_size, out_off, modelblob, results,
-        seg_recs, misc, heads, plain, pool;
-    // pinned host staging for small read-backs
-    void *pinned = nullptr;
-    size_t pinned_cap = 0;
-    // streaming-shaped state (compressor.v:6-8 state machine)
-    int st_state = 2;  // 0 block, 1 segment, 2 start
-    Model st_model;
-    std::vector<PendingSeg> st_segs;
-    std::vector<uint8_t> st_done;  // finished block kept until the caller's buffer is large enough
-    bool st_has_done = false;
-};
-
-namespace {
-
-#define CK(call)                                                                              \
-    do {                                                                                      \
-        cudaError_t e_ = (call);                                                              \
-        if (e_ != cudaSuccess) {                                                              \
-            ctx->err = std::string(#call) + ": " + cudaGetErrorString(e_);                    \
-            return ZPAQGPU_E_CUDA;                                                            \
-        }                                                                                     \
-    } while (0)
+namespace zg {
 
 int ensure(zpaqgpu_ctx *ctx, DevBuf &b, size_t bytes) {
     if (bytes <= b.cap) return ZPAQGPU_OK;
@@ -253,19 +193,6 @@ float elapsed(cudaEvent_t a, cudaEvent_t b) {
 // ------------------------------------------------------------------------------------------
 // Compression job: blocks of segments, plaintext already on the device.
 // ------------------------------------------------------------------------------------------
-struct CompressJob {
-    const Model *model;
-    std::vector<EncBlock> blocks;
-    std::vector<SegSpec> segs;
-    const u8 *d_in;       // plaintext on the device
-    u8 *d_out;            // where the archive bytes go (device)
-    u64 out_cap;
-    u64 *d_out_off;       // device, n_blocks+1
-    // results
-    u64 total = 0;
-    bool fits = true;
-};
-
 int run_compress(zpaqgpu_ctx *ctx, CompressJob &job) {
     const Model &m = *job.model;
     const int n_blocks = int(job.blocks.size()), n_segs = int(job.segs.size());
@@ -853,7 +780,9 @@ void zpaqgpu_destroy(zpaqgpu_ctx *ctx) {
     if (ctx->own_stream) cudaStreamSynchronize(ctx->own_stream);
     DevBuf *bufs[] = {&ctx->workspace, &ctx->in, &ctx->arena, &ctx->out, &ctx->desc, &ctx->pay_len,
                       &ctx->digests, &ctx->seg_size, &ctx->out_off, &ctx->modelblob, &ctx->results,
-                      &ctx->seg_recs, &ctx->misc, &ctx->heads, &ctx->plain, &ctx->pool};
+                      &ctx->seg_recs, &ctx->misc, &ctx->heads, &ctx->plain, &ctx->pool,
+                      &ctx->jd_in, &ctx->jd_frag, &ctx->jd_tab, &ctx->jd_packed, &ctx->jd_small,
+                      &ctx->jd_out2, &ctx->jd_off2};
     for (DevBuf *b : bufs)
         if (b->p) cudaFree(b->p);
     if (ctx->tables_mem) cudaFree(ctx->tables_mem);

@@ -1,0 +1,610 @@
+// jidac.cu -- the jidac front end of libzpaqgpu: content-defined fragmentation, SHA-1 of every
+// fragment, deduplication, and assembly of a journaling archive (c / d / h / i blocks) in the
+// layout JidacArchive.create_archive writes (jidac.v:181-296).
+//
+// Stages, each its own kernel (all integer/byte work, HBM- or latency-bound, no tensor cores):
+//   k_fragment_files   one thread per file walks its bytes with upstream zpaq's rolling hash
+//                      (order-1 prediction table o1[256] per thread in shared memory)
+//   k_frag_scan/_emit  per-file fragment counts -> one fragment list in file order
+//   k_sha1_segments    SHA-1 per fragment (kernels_aux.cu, sha1.v:42-146)
+//   k_dedup_insert/_resolve   open-addressing table keyed by the digest; the representative of a
+//                      group of equal fragments is the smallest fragment index (deterministic ids)
+//   k_frag_ids         stored flags, 1-based ids (jidac.v:153-163) and packed offsets, one scan
+//   k_gather_fragments stored fragments back to back: the plaintext of the d blocks
+// The d blocks then go through the same run_compress job as zpaqgpu_compress_blocks, the c/h/i
+// blocks through the store-mode path of the same job (compressor.v:297-354).
+#include <algorithm>
+#include <cstring>
+#include <numeric>
+#include <string>
+#include <vector>
+
+#include "ctx.h"
+
+using namespace zg;
+
+namespace zg {
+namespace {
+
+constexpr int kFragThreads = 64;
+constexpr u32 kEmpty = 0xFFFFFFFFu;
+
+struct FragArgs {
+    const u8 *in;
+    const u64 *file_off;  // n_files + 1, relative to `in`
+    const u32 *order;     // file handled by thread t: longest files first, so that the lanes of a
+                          // warp walk files of similar length
+    int n_files;
+    int fragment;
+    const u64 *cap_off;   // first record slot of each file
+    u64 *ends;            // fragment end offsets, slot cap_off[f] + j
+    u32 *count;           // fragments per file
+};
+
+// Upstream zpaq's cut rule (restated from memory of zpaq 7.15 `add`; not part of the reference, so
+// parity is unpinned; the test suite checks this kernel against a separate CPU statement of the
+// same rule): per fragment,
+//   h = (h + c + 1) * (c == o1[c1] ? 314159265 : 271828182);  o1[c1] = c;  c1 = c
+// and the fragment ends at EOF, at 8128<<fragment bytes, or when h < 2^(22-fragment) after at least
+// 64<<fragment bytes.  h, c1 and o1 start from zero in every fragment, which makes the fragments of
+// one file a serial chain; parallelism is across files.
+__global__ void __launch_bounds__(kFragThreads) k_fragment_files(FragArgs A) {
+    __shared__ u8 o1[256 * kFragThreads];
+    const int t = blockIdx.x * kFragThreads + threadIdx.x;
+    if (t >= A.n_files) return;
+    const u32 f = A.order[t];
+    const u64 lo = A.file_off[f], hi = A.file_off[f + 1];
+    u64 *ends = A.ends + A.cap_off[f];
+    if (A.fragment < 0) {  // jidac.v:191-200: the whole file is one fragment, an empty file too
+        ends[0] = hi;
+        A.count[f] = 1;
+        return;
+    }
+    const u64 minf = 64ull << A.fragment, maxf = 8128ull << A.fragment;
+    const bool hashed = A.fragment <= 22;
+    const u32 thresh = hashed ? (1u << (22 - A.fragment)) : 0u;
+    u8 *mine = o1 + threadIdx.x;
+    const u8 *in = A.in;
+    u32 cnt = 0;
+    u64 pos = lo;
+    while (pos < hi) {
+        for (int k = 0; k < 256; ++k) mine[k * kFragThreads] = 0;
+        u32 h = 0, c1 = 0;
+        const u64 stop = min(hi, pos + maxf), earliest = pos + minf;
+        while (pos < stop) {
+            const u32 c = __ldg(in + pos);
+            ++pos;
+            const u32 pred = mine[c1 * kFragThreads];
+            h = (h + c + 1u) * (c == pred ? 314159265u : 271828182u);
+            mine[c1 * kFragThreads] = u8(c);
+            c1 = c;
+            if (hashed && h < thresh && pos >= earliest) break;
+        }
+        ends[cnt++] = pos;
+    }
+    A.count[f] = cnt;
+}
+
+// single CTA: base[] = exclusive prefix sum of count[], base[n] = total
+__global__ void k_frag_scan(const u32 *count, int n, u32 *base) {
+    __shared__ u32 partial[1024];
+    const int t = threadIdx.x, nt = blockDim.x;
+    const int per = (n + nt - 1) / nt;
+    const int lo = min(n, t * per), hi = min(n, lo + per);
+    u32 sum = 0;
+    for (int i = lo; i < hi; ++i) sum += count[i];
+    partial[t] = sum;
+    __syncthreads();
+    if (t == 0) {
+        u32 run = 0;
+        for (int i = 0; i < nt; ++i) {
+            const u32 v = partial[i];
+            partial[i] = run;
+            run += v;
+        }
+        base[n] = run;
+    }
+    __syncthreads();
+    u32 at = partial[t];
+    for (int i = lo; i < hi; ++i) {
+        base[i] = at;
+        at += count[i];
+    }
+}
+
+__global__ void k_frag_emit(const u64 *file_off, const u64 *cap_off, const u64 *ends, const u32 *count,
+                            const u32 *base, int n_files, ShaJob *jobs, u32 *file_of) {
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= n_files) return;
+    u64 start = file_off[f];
+    const u64 *e = ends + cap_off[f];
+    const u32 n = count[f], b = base[f];
+    for (u32 j = 0; j < n; ++j) {
+        jobs[b + j].off = start, jobs[b + j].len = e[j] - start;
+        file_of[b + j] = u32(f);
+        start = e[j];
+    }
+}
+
+__device__ __forceinline__ bool same_fragment(const u8 *digests, const ShaJob *jobs, u32 a, u32 b) {
+    if (jobs[a].len != jobs[b].len) return false;
+    const u32 *x = reinterpret_cast<const u32 *>(digests + u64(a) * 20);
+    const u32 *y = reinterpret_cast<const u32 *>(digests + u64(b) * 20);
+    return x[0] == y[0] && x[1] == y[1] && x[2] == y[2] && x[3] == y[3] && x[4] == y[4];
+}
+
+// Every group of equal fragments ends up owning one table slot that holds its smallest index.
+__global__ void k_dedup_insert(const u8 *digests, const ShaJob *jobs, u32 n, u32 *tab, u32 mask) {
+    const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    u32 s = *reinterpret_cast<const u32 *>(digests + u64(i) * 20) & mask;
+    for (;;) {
+        const u32 cur = atomicCAS(&tab[s], kEmpty, i);
+        if (cur == kEmpty) return;
+        if (same_fragment(digests, jobs, cur, i)) {
+            atomicMin(&tab[s], i);
+            return;
+        }
+        s = (s + 1) & mask;
+    }
+}
+
+__global__ void k_dedup_resolve(const u8 *digests, const ShaJob *jobs, u32 n, const u32 *tab, u32 mask,
+                                u32 *rep) {
+    const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    u32 s = *reinterpret_cast<const u32 *>(digests + u64(i) * 20) & mask;
+    for (;;) {
+        const u32 cur = tab[s];
+        if (cur == kEmpty || same_fragment(digests, jobs, cur, i)) {  // kEmpty cannot happen after insert
+            rep[i] = cur == kEmpty ? i : cur;
+            return;
+        }
+        s = (s + 1) & mask;
+    }
+}
+
+__global__ void k_iota(u32 *rep, u32 n) {
+    const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) rep[i] = i;
+}
+
+// single CTA: stored[i] = (rep[i] == i); ids count stored fragments from 1 in list order
+// (a.fragments.len after the push, jidac.v:153-163); pack_off = bytes of stored fragments before i;
+// duplicates take the id of their representative.  totals = {n_stored, stored_bytes}.
+__global__ void k_frag_ids(const ShaJob *jobs, const u32 *rep, u32 n, u32 *stored, u32 *id, u64 *pack_off,
+                           u64 *totals) {
+    __shared__ u32 pc[1024];
+    __shared__ u64 pb[1024];
+    const u32 t = threadIdx.x, nt = blockDim.x;
+    const u32 per = (n + nt - 1) / nt;
+    const u32 lo = min(n, t * per), hi = min(n, lo + per);
+    u32 c = 0;
+    u64 b = 0;
+    for (u32 i = lo; i < hi; ++i)
+        if (rep[i] == i) ++c, b += jobs[i].len;
+    pc[t] = c, pb[t] = b;
+    __syncthreads();
+    if (t == 0) {
+        u32 rc = 0;
+        u64 rb = 0;
+        for (u32 k = 0; k < nt; ++k) {
+            const u32 vc = pc[k];
+            const u64 vb = pb[k];
+            pc[k] = rc, pb[k] = rb;
+            rc += vc, rb += vb;
+        }
+        totals[0] = rc, totals[1] = rb;
+    }
+    __syncthreads();
+    c = pc[t], b = pb[t];
+    for (u32 i = lo; i < hi; ++i) {
+        const bool s = rep[i] == i;
+        stored[i] = s ? 1u : 0u;
+        pack_off[i] = b;
+        if (s) id[i] = ++c, b += jobs[i].len;
+    }
+    __syncthreads();
+    __threadfence_block();
+    for (u32 i = lo; i < hi; ++i)
+        if (rep[i] != i) id[i] = id[rep[i]];
+}
+
+__global__ void k_gather_fragments(const u8 *in, const ShaJob *jobs, const u32 *stored, const u64 *pack_off,
+                                   u8 *dst) {
+    const u32 i = blockIdx.x;
+    if (!stored[i]) return;
+    const u8 *s = in + jobs[i].off;
+    u8 *d = dst + pack_off[i];
+    const u64 len = jobs[i].len;
+    // 16-byte copies when source and destination are congruent mod 16, bytes otherwise
+    if (((reinterpret_cast<uintptr_t>(s) ^ reinterpret_cast<uintptr_t>(d)) & 15) == 0) {
+        const u64 head = min(len, u64((16 - (reinterpret_cast<uintptr_t>(s) & 15)) & 15));
+        for (u64 k = threadIdx.x; k < head; k += blockDim.x) d[k] = s[k];
+        const u64 vec = (len - head) / 16;
+        const uint4 *sv = reinterpret_cast<const uint4 *>(s + head);
+        uint4 *dv = reinterpret_cast<uint4 *>(d + head);
+        for (u64 k = threadIdx.x; k < vec; k += blockDim.x) dv[k] = sv[k];
+        for (u64 k = head + vec * 16 + threadIdx.x; k < len; k += blockDim.x) d[k] = s[k];
+    } else {
+        for (u64 k = threadIdx.x; k < len; k += blockDim.x) d[k] = s[k];
+    }
+}
+
+// ---- host side ---------------------------------------------------------------------------
+
+struct Front {
+    int n_frags = 0, n_stored = 0;
+    u64 stored_bytes = 0, total_in = 0;
+    std::vector<ShaJob> jobs;  // ranges relative to the first input byte
+    std::vector<u32> file_of, id, stored;
+    std::vector<u64> pack_off;
+    std::vector<u8> digests;
+    const u8 *d_plain = nullptr;  // device: stored fragments back to back in id order
+};
+
+struct Timer {
+    cudaEvent_t a = nullptr, b = nullptr;
+    Timer() { cudaEventCreate(&a), cudaEventCreate(&b); }
+    ~Timer() {
+        if (a) cudaEventDestroy(a);
+        if (b) cudaEventDestroy(b);
+    }
+    void start(cudaStream_t s) { cudaEventRecord(a, s); }
+    void stop(cudaStream_t s) { cudaEventRecord(b, s); }
+    float ms() {
+        cudaEventSynchronize(b);
+        return elapsed(a, b);
+    }
+};
+
+int jidac_front(zpaqgpu_ctx *ctx, const uint8_t *in, const uint64_t *in_off, int n_files, int fragment, int dedup,
+                bool gather, Front &R) {
+    zpaqgpu_jidac_stats &S = ctx->jd_stats;
+    S = zpaqgpu_jidac_stats{};
+    S.n_files = n_files;
+    if (n_files == 0) return ZPAQGPU_OK;
+    cudaStream_t st = ctx->stream;
+    const u64 base = in_off[0];
+    R.total_in = in_off[n_files] - base;
+    S.input_bytes = R.total_in;
+    if (R.total_in && !in) return ZPAQGPU_E_ARG;
+    int rc;
+    if ((rc = ensure(ctx, ctx->jd_in, std::max<u64>(R.total_in, 16)))) return rc;
+    Timer t_h2d, t_frag, t_sha, t_dedup, t_gather;
+    t_h2d.start(st);
+    if (R.total_in) CK(cudaMemcpyAsync(ctx->jd_in.p, in + base, R.total_in, cudaMemcpyHostToDevice, st));
+    t_h2d.stop(st);
+
+    // per-file tables: offsets, processing order (longest first), record capacity
+    const size_t nf = size_t(n_files);
+    std::vector<u64> file_off(nf + 1), cap_off(nf + 1);
+    std::vector<u32> order(nf);
+    const u64 minf = fragment < 0 ? 0 : (64ull << std::min(fragment, 40));
+    u64 cap_total = 0;
+    for (size_t f = 0; f <= nf; ++f) {
+        if (f && in_off[f] < in_off[f - 1]) return ZPAQGPU_E_ARG;
+        file_off[f] = in_off[f] - base;
+    }
+    for (size_t f = 0; f < nf; ++f) {
+        cap_off[f] = cap_total;
+        const u64 len = file_off[f + 1] - file_off[f];
+        cap_total += fragment < 0 ? 1 : len / minf + 1;
+    }
+    cap_off[nf] = cap_total;
+    if (cap_total >= 0xFFFFFFF0ull) {
+        ctx->err = "too many fragments for one call";
+        return ZPAQGPU_E_ARG;
+    }
+    std::iota(order.begin(), order.end(), 0u);
+    std::stable_sort(order.begin(), order.end(), [&](u32 a, u32 b) {
+        return file_off[a + 1] - file_off[a] > file_off[b + 1] - file_off[b];
+    });
+    // device layout of the fragment tables
+    const size_t ct = std::max<size_t>(size_t(cap_total), 1);
+    size_t at = 0;
+    auto take = [&](size_t bytes) { const size_t o = at; at = align_up(at + bytes, 16); return o; };
+    const size_t o_foff = take(8 * (nf + 1)), o_coff = take(8 * (nf + 1)), o_order = take(4 * nf);
+    const size_t o_count = take(4 * nf), o_base = take(4 * (nf + 1));
+    const size_t o_ends = take(8 * ct), o_jobs = take(sizeof(ShaJob) * ct), o_file = take(4 * ct);
+    const size_t o_rep = take(4 * ct), o_id = take(4 * ct), o_stored = take(4 * ct), o_pack = take(8 * ct);
+    const size_t o_dig = take(20 * ct + 16), o_tot = take(16);
+    if ((rc = ensure(ctx, ctx->jd_frag, at))) return rc;
+    u8 *fb = static_cast<u8 *>(ctx->jd_frag.p);
+    CK(cudaMemcpyAsync(fb + o_foff, file_off.data(), 8 * (nf + 1), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(fb + o_coff, cap_off.data(), 8 * (nf + 1), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(fb + o_order, order.data(), 4 * nf, cudaMemcpyHostToDevice, st));
+    const u8 *d_in = static_cast<const u8 *>(ctx->jd_in.p);
+    ShaJob *d_jobs = reinterpret_cast<ShaJob *>(fb + o_jobs);
+    u32 *d_rep = reinterpret_cast<u32 *>(fb + o_rep), *d_id = reinterpret_cast<u32 *>(fb + o_id);
+    u32 *d_stored = reinterpret_cast<u32 *>(fb + o_stored), *d_base = reinterpret_cast<u32 *>(fb + o_base);
+    u64 *d_pack = reinterpret_cast<u64 *>(fb + o_pack);
+    u8 *d_dig = fb + o_dig;
+
+    t_frag.start(st);
+    FragArgs fa;
+    fa.in = d_in, fa.file_off = reinterpret_cast<const u64 *>(fb + o_foff);
+    fa.order = reinterpret_cast<const u32 *>(fb + o_order), fa.n_files = n_files, fa.fragment = fragment;
+    fa.cap_off = reinterpret_cast<const u64 *>(fb + o_coff), fa.ends = reinterpret_cast<u64 *>(fb + o_ends);
+    fa.count = reinterpret_cast<u32 *>(fb + o_count);
+    k_fragment_files<<<(n_files + kFragThreads - 1) / kFragThreads, kFragThreads, 0, st>>>(fa);
+    k_frag_scan<<<1, 1024, 0, st>>>(fa.count, n_files, d_base);
+    k_frag_emit<<<(n_files + 127) / 128, 128, 0, st>>>(fa.file_off, fa.cap_off, fa.ends, fa.count, d_base, n_files,
+                                                       d_jobs, reinterpret_cast<u32 *>(fb + o_file));
+    t_frag.stop(st);
+    CK(cudaGetLastError());
+    u32 n_frags = 0;
+    CK(cudaMemcpyAsync(&n_frags, d_base + n_files, 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    S.launches += 3;
+    R.n_frags = int(n_frags);
+    S.n_fragments = R.n_frags;
+    S.fragment_ms = t_frag.ms();
+    S.h2d_ms = t_h2d.ms();
+    if (n_frags == 0) return ZPAQGPU_OK;
+
+    t_sha.start(st);
+    launch_sha1(d_in, d_jobs, int(n_frags), d_dig, st);
+    t_sha.stop(st);
+    S.launches += 1;
+
+    t_dedup.start(st);
+    const u32 grid = (n_frags + 255) / 256;
+    if (dedup) {
+        u32 slots = 64;
+        while (slots < 2 * n_frags) slots <<= 1;
+        if ((rc = ensure(ctx, ctx->jd_tab, 4 * size_t(slots)))) return rc;
+        CK(cudaMemsetAsync(ctx->jd_tab.p, 0xFF, 4 * size_t(slots), st));
+        u32 *tab = static_cast<u32 *>(ctx->jd_tab.p);
+        k_dedup_insert<<<grid, 256, 0, st>>>(d_dig, d_jobs, n_frags, tab, slots - 1);
+        k_dedup_resolve<<<grid, 256, 0, st>>>(d_dig, d_jobs, n_frags, tab, slots - 1, d_rep);
+        S.launches += 3;
+    } else {
+        k_iota<<<grid, 256, 0, st>>>(d_rep, n_frags);
+        S.launches += 1;
+    }
+    k_frag_ids<<<1, 1024, 0, st>>>(d_jobs, d_rep, n_frags, d_stored, d_id, d_pack,
+                                   reinterpret_cast<u64 *>(fb + o_tot));
+    t_dedup.stop(st);
+    S.launches += 1;
+    CK(cudaGetLastError());
+
+    R.jobs.resize(n_frags), R.file_of.resize(n_frags), R.id.resize(n_frags), R.stored.resize(n_frags);
+    R.pack_off.resize(n_frags), R.digests.resize(20 * size_t(n_frags));
+    u64 totals[2] = {0, 0};
+    CK(cudaMemcpyAsync(R.jobs.data(), d_jobs, sizeof(ShaJob) * n_frags, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(R.file_of.data(), fb + o_file, 4 * size_t(n_frags), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(R.id.data(), d_id, 4 * size_t(n_frags), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(R.stored.data(), d_stored, 4 * size_t(n_frags), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(R.pack_off.data(), d_pack, 8 * size_t(n_frags), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(R.digests.data(), d_dig, 20 * size_t(n_frags), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(totals, fb + o_tot, 16, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    R.n_stored = int(totals[0]), R.stored_bytes = totals[1];
+    S.n_stored = R.n_stored, S.stored_bytes = R.stored_bytes;
+    S.sha1_ms = t_sha.ms(), S.dedup_ms = t_dedup.ms();
+
+    R.d_plain = d_in;  // without duplicates the fragments tile the input: pack_off == off
+    if (gather && R.n_stored != R.n_frags) {
+        if ((rc = ensure(ctx, ctx->jd_packed, std::max<u64>(R.stored_bytes, 16)))) return rc;
+        t_gather.start(st);
+        k_gather_fragments<<<n_frags, 256, 0, st>>>(d_in, d_jobs, d_stored, d_pack, static_cast<u8 *>(ctx->jd_packed.p));
+        t_gather.stop(st);
+        CK(cudaGetLastError());
+        S.launches += 1;
+        S.gather_ms = t_gather.ms();
+        R.d_plain = static_cast<const u8 *>(ctx->jd_packed.p);
+    }
+    return ZPAQGPU_OK;
+}
+
+// itos_pad / make_jidac_filename (jidac.v:38-49)
+std::string pad_num(long long n, int width) {
+    std::string s = std::to_string(n);
+    while (int(s.size()) < width) s = "0" + s;
+    return s;
+}
+std::string jidac_name(long long date, char type, u32 num) {
+    return "jDC" + pad_num(date, 14) + std::string(1, type) + pad_num(num, 10);
+}
+std::string jidac_comment(u64 usize) { return std::to_string(usize) + " jDC\x01"; }  // jidac.v:69, :96
+void put_le(std::vector<u8> &v, u64 x, int bytes) {
+    for (int i = 0; i < bytes; ++i) v.push_back(u8(x >> (8 * i)));
+}
+
+struct DBlock {
+    u32 first_id, n;
+    u64 off, len;        // inside the packed plaintext
+    std::vector<u32> frags;  // fragment list indices
+};
+
+}  // namespace
+}  // namespace zg
+
+extern "C" {
+
+int zpaqgpu_jidac_last_stats(const zpaqgpu_ctx *ctx, zpaqgpu_jidac_stats *out) {
+    if (!ctx || !out) return ZPAQGPU_E_ARG;
+    *out = ctx->jd_stats;
+    return ZPAQGPU_OK;
+}
+
+int zpaqgpu_jidac_fragment(zpaqgpu_ctx *ctx, const uint8_t *in, const uint64_t *in_off, int n_files, int fragment,
+                           int dedup, zpaqgpu_fragment *frags, int cap, int *n_frags, int *n_stored) {
+    if (!ctx || n_files < 0 || (n_files > 0 && !in_off) || !n_frags) return ZPAQGPU_E_ARG;
+    CK(cudaSetDevice(ctx->device));
+    Front R;
+    const int rc = jidac_front(ctx, in, in_off, n_files, fragment, dedup, false, R);
+    if (rc) return rc;
+    *n_frags = R.n_frags;
+    if (n_stored) *n_stored = R.n_stored;
+    if (R.n_frags > cap) return ZPAQGPU_E_NOSPACE;
+    if (R.n_frags && !frags) return ZPAQGPU_E_ARG;
+    const u64 base = n_files ? in_off[0] : 0;
+    for (int i = 0; i < R.n_frags; ++i) {
+        zpaqgpu_fragment &f = frags[i];
+        f.off = R.jobs[size_t(i)].off + base, f.len = R.jobs[size_t(i)].len;
+        f.file = R.file_of[size_t(i)], f.id = R.id[size_t(i)], f.stored = R.stored[size_t(i)];
+        std::memcpy(f.sha1, R.digests.data() + 20 * size_t(i), 20);
+    }
+    return ZPAQGPU_OK;
+}
+
+int zpaqgpu_jidac_add(zpaqgpu_ctx *ctx, const zpaqgpu_jidac_opts *opts, const char *const *names, const uint8_t *in,
+                      const uint64_t *in_off, int n_files, uint8_t *out, uint64_t out_cap, uint64_t *out_len,
+                      uint64_t *out_need) {
+    if (!ctx || !opts || n_files < 0 || (n_files > 0 && (!in_off || !names))) return ZPAQGPU_E_ARG;
+    if (opts->level < 0 || opts->level > 5) return ZPAQGPU_E_ARG;
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    Front R;
+    int rc = jidac_front(ctx, in, in_off, n_files, opts->fragment, opts->dedup, true, R);
+    if (rc) return rc;
+    zpaqgpu_jidac_stats S = ctx->jd_stats;  // run_compress below does not touch jd_stats
+
+    // ---- d blocks: stored fragments in id order, packed up to block_bytes (jidac.v:186-214) ----
+    std::vector<DBlock> dblocks;
+    for (int i = 0; i < R.n_frags; ++i) {
+        if (!R.stored[size_t(i)]) continue;
+        const u64 len = R.jobs[size_t(i)].len;
+        const bool fresh = dblocks.empty() || opts->block_bytes == 0 || dblocks.back().len + len > opts->block_bytes;
+        if (fresh) dblocks.push_back(DBlock{R.id[size_t(i)], 0, R.pack_off[size_t(i)], 0, {}});
+        DBlock &b = dblocks.back();
+        b.n++, b.len += len, b.frags.push_back(u32(i));
+    }
+    const int nd = int(dblocks.size());
+    S.n_dblocks = nd;
+    std::vector<u64> d_off(size_t(nd) + 1, 0);
+    u64 total_d = 0;
+    if (nd) {
+        const std::vector<uint8_t> h = level_header(opts->level);
+        Model m;
+        if ((rc = model_from_level_layout(h.data(), int(h.size()), m))) return ctx->err = m.error, rc;
+        CompressJob job;
+        job.model = &m;
+        job.blocks.resize(size_t(nd)), job.segs.resize(size_t(nd));
+        std::vector<std::string> nm(static_cast<size_t>(nd)), cm(static_cast<size_t>(nd));
+        u64 worst = 0;
+        for (int b = 0; b < nd; ++b) {
+            const DBlock &d = dblocks[size_t(b)];
+            nm[size_t(b)] = jidac_name(opts->date, 'd', d.first_id);
+            cm[size_t(b)] = jidac_comment(d.len);
+            job.blocks[size_t(b)] = EncBlock{u32(b), 1};
+            SegSpec &sp = job.segs[size_t(b)];
+            sp.name = nm[size_t(b)].c_str(), sp.comment = cm[size_t(b)].c_str();
+            sp.in_off = d.off, sp.in_len = d.len, sp.called = true;  // jidac.v:112 always calls compress()
+            worst += d.len + d.len / 2 + 2048;
+        }
+        if ((rc = ensure(ctx, ctx->out, worst))) return rc;
+        if ((rc = ensure(ctx, ctx->out_off, 8 * size_t(nd + 1)))) return rc;
+        job.d_in = R.d_plain;
+        job.d_out = static_cast<u8 *>(ctx->out.p), job.out_cap = ctx->out.cap;
+        job.d_out_off = static_cast<u64 *>(ctx->out_off.p);
+        if ((rc = run_compress(ctx, job))) return rc;
+        S.codec_ms += ctx->stats.codec_ms, S.pack_ms += ctx->stats.pack_ms, S.sha1_ms += ctx->stats.sha1_ms;
+        S.launches += ctx->stats.launches;
+        if (!job.fits) {
+            if ((rc = ensure(ctx, ctx->out, job.total))) return rc;
+            job.d_out = static_cast<u8 *>(ctx->out.p), job.out_cap = ctx->out.cap;
+            if ((rc = run_compress(ctx, job))) return rc;
+            S.codec_ms += ctx->stats.codec_ms, S.launches += ctx->stats.launches;
+        }
+        total_d = job.total;
+        CK(cudaMemcpyAsync(d_off.data(), ctx->out_off.p, 8 * size_t(nd + 1), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+    }
+
+    // ---- c, h and i blocks, all store mode (jidac.v:67-91, :216-295) ----
+    std::vector<u8> small;                 // their plaintext back to back
+    std::vector<u64> s_off{0};
+    std::vector<std::string> s_name, s_comment;
+    auto close_block = [&](char type, u32 num) {
+        s_name.push_back(jidac_name(opts->date, type, num));
+        s_comment.push_back(jidac_comment(small.size() - s_off.back()));
+        s_off.push_back(small.size());
+    };
+    put_le(small, total_d, 8);             // c block: bytes of all d blocks (jidac.v:217-219)
+    close_block('c', u32(R.n_stored) + 1);
+    for (int b = 0; b < nd; ++b) {         // h blocks: bsize[4] (sha1[20] usize[4])... (jidac.v:229-259)
+        const DBlock &d = dblocks[size_t(b)];
+        put_le(small, u32(d_off[size_t(b) + 1] - d_off[size_t(b)]), 4);
+        for (u32 i : d.frags) {
+            small.insert(small.end(), R.digests.begin() + 20 * size_t(i), R.digests.begin() + 20 * size_t(i) + 20);
+            put_le(small, u32(R.jobs[i].len), 4);
+        }
+        close_block('h', d.first_id);
+    }
+    {                                      // i block: date[8] filename 0 na[4] ni[4] ptr[ni][4] (jidac.v:262-295)
+        size_t fi = 0;
+        for (int f = 0; f < n_files; ++f) {
+            put_le(small, u64(opts->date), 8);
+            for (const char *c = names[f] ? names[f] : ""; *c; ++c) small.push_back(u8(*c));
+            small.push_back(0);
+            size_t fe = fi;
+            while (fe < size_t(R.n_frags) && R.file_of[fe] == u32(f)) ++fe;
+            if (opts->date != 0) {
+                put_le(small, 0, 4);
+                put_le(small, u32(fe - fi), 4);
+                for (size_t k = fi; k < fe; ++k) put_le(small, R.id[k], 4);
+            }
+            fi = fe;
+        }
+        if (small.size() > s_off.back()) close_block('i', 1);
+    }
+    const int ns = int(s_name.size());
+    std::vector<u64> o2(size_t(ns) + 1, 0);
+    u64 total_s = 0;
+    {
+        const std::vector<uint8_t> h = level_header(0);
+        Model m0;
+        if ((rc = model_from_level_layout(h.data(), int(h.size()), m0))) return ctx->err = m0.error, rc;
+        if ((rc = ensure(ctx, ctx->jd_small, small.size() + 16))) return rc;
+        CK(cudaMemcpyAsync(ctx->jd_small.p, small.data(), small.size(), cudaMemcpyHostToDevice, st));
+        CompressJob job;
+        job.model = &m0;
+        job.blocks.resize(size_t(ns)), job.segs.resize(size_t(ns));
+        for (int b = 0; b < ns; ++b) {
+            job.blocks[size_t(b)] = EncBlock{u32(b), 1};
+            SegSpec &sp = job.segs[size_t(b)];
+            sp.name = s_name[size_t(b)].c_str(), sp.comment = s_comment[size_t(b)].c_str();
+            sp.in_off = s_off[size_t(b)], sp.in_len = s_off[size_t(b) + 1] - s_off[size_t(b)], sp.called = true;
+        }
+        const u64 cap2 = small.size() + small.size() / 4096 + 256 * u64(ns) + 4096;
+        if ((rc = ensure(ctx, ctx->jd_out2, cap2))) return rc;
+        if ((rc = ensure(ctx, ctx->jd_off2, 8 * size_t(ns + 1)))) return rc;
+        job.d_in = static_cast<const u8 *>(ctx->jd_small.p);
+        job.d_out = static_cast<u8 *>(ctx->jd_out2.p), job.out_cap = ctx->jd_out2.cap;
+        job.d_out_off = static_cast<u64 *>(ctx->jd_off2.p);
+        if ((rc = run_compress(ctx, job))) return rc;
+        S.launches += ctx->stats.launches, S.pack_ms += ctx->stats.pack_ms;
+        if (!job.fits) {
+            ctx->err = "index blocks larger than their bound";
+            return ZPAQGPU_E_CUDA;
+        }
+        total_s = job.total;
+        CK(cudaMemcpyAsync(o2.data(), ctx->jd_off2.p, 8 * size_t(ns + 1), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+    }
+    const u64 total = total_d + total_s;
+    S.archive_bytes = total;
+    if (out_len) *out_len = total;
+    if (out_need) *out_need = total;
+    ctx->jd_stats = S;
+    if (total > out_cap) return ZPAQGPU_E_NOSPACE;
+    if (!out) return ZPAQGPU_E_ARG;
+    // archive order: c block, d blocks, h blocks, i block (jidac.v:221-295)
+    Timer t_d2h;
+    t_d2h.start(st);
+    const u64 c_len = o2[1];
+    const u8 *s2 = static_cast<const u8 *>(ctx->jd_out2.p);
+    CK(cudaMemcpyAsync(out, s2, c_len, cudaMemcpyDeviceToHost, st));
+    if (total_d) CK(cudaMemcpyAsync(out + c_len, ctx->out.p, total_d, cudaMemcpyDeviceToHost, st));
+    if (total_s > c_len)
+        CK(cudaMemcpyAsync(out + c_len + total_d, s2 + c_len, total_s - c_len, cudaMemcpyDeviceToHost, st));
+    t_d2h.stop(st);
+    CK(cudaStreamSynchronize(st));
+    ctx->jd_stats.d2h_ms = t_d2h.ms();
+    return ZPAQGPU_OK;
+}
+
+}  // extern "C"
