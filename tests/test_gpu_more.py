@@ -137,10 +137,15 @@ def test_waves_when_tables_do_not_fit(gpu_ctx):
     blocks = [datagen.text(20000, datagen.SEED0 + k) for k in range(8)]
     want = [ob.compress_block(2, b, "", "") for b in blocks]
     gpu_ctx.set_workspace_limit(3 * 12656896 + 4096)
-    got = gpu_ctx.compress_blocks(2, blocks)
-    assert got == want and gpu_ctx.stats()["waves"] == 3
-    plain, segs, status = gpu_ctx.decompress_archive(b"".join(got))
-    assert status == 0 and plain == b"".join(blocks) and gpu_ctx.stats()["waves"] == 3
+    gpu_ctx.set_table_mode(1)  # dense tables: in auto mode a batch that does not fit is paged instead
+    try:
+        got = gpu_ctx.compress_blocks(2, blocks)
+        assert got == want and gpu_ctx.stats()["waves"] == 3
+        plain, segs, status = gpu_ctx.decompress_archive(b"".join(got))
+        assert status == 0 and plain == b"".join(blocks) and gpu_ctx.stats()["waves"] == 3
+    finally:
+        gpu_ctx.set_table_mode(0)
+        gpu_ctx.set_workspace_limit(0)
 
 
 def test_full_size_roundtrip_properties(gpu_ctx):

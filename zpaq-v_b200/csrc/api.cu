@@ -2,6 +2,7 @@
 // wave scheduling over the table workspace and the host side of block framing.
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
@@ -562,7 +563,7 @@ int run_decompress(zpaqgpu_ctx *ctx, DecompressJob &job, bool caller_owns_plain)
                                 if ((rc = prepare_wave(ctx, mod, tp, cnt, da.model))) return rc;
                                 CK(cudaEventRecord(ctx->ev[1], st));
                                 if (chain) {
-                                    if (!launch_decode_chain(m, da, wpc, st)) {
+                                    if (!launch_decode_chain(m, da, wpc, ctx->tree_decoder, st)) {
                                         ctx->err = "no chain kernel instantiation for this model";
                                         return ZPAQGPU_E_UNSUPPORTED;
                                     }
@@ -725,6 +726,7 @@ int zpaqgpu_init(zpaqgpu_ctx **out, int device) {
     if (cudaSetDevice(device) != cudaSuccess) return ZPAQGPU_E_NODEVICE;
     zpaqgpu_ctx *ctx = new zpaqgpu_ctx();
     ctx->device = device;
+    if (const char *v = std::getenv("ZPAQGPU_DECODER")) ctx->tree_decoder = std::strcmp(v, "serial") != 0;
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->sm_count = prop.multiProcessorCount;
     bool ok = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) == cudaSuccess &&

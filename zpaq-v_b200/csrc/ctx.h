@@ -38,6 +38,7 @@ struct zpaqgpu_ctx {
     void *tables_mem = nullptr;
     int kernel_pref = ZPAQGPU_KERNEL_AUTO;
     int table_mode = ZPAQGPU_TABLES_AUTO;
+    bool tree_decoder = true;  // ZPAQGPU_DECODER=serial in the environment selects the one-bit-at-a-time decoder
     zg::u64 ws_limit = 0;
     int sm_count = 148;
     std::string err;

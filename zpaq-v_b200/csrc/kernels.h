@@ -44,7 +44,8 @@ __global__ void k_decode_generic(DecodeArgs A);
 bool launch_encode_pipe3(const Model &m, const EncodeArgs &A, int blocks_per_cta, cudaStream_t s);
 size_t encpipe_smem_bytes(const Model &m, int blocks_per_cta);
 int encpipe_max_blocks_per_cta(const Model &m);
-bool launch_decode_chain(const Model &m, const DecodeArgs &A, int warps_per_cta, cudaStream_t s);
+// tree: speculative whole-nibble decoder (one lane per tree node and outcome) instead of the serial one
+bool launch_decode_chain(const Model &m, const DecodeArgs &A, int warps_per_cta, bool tree, cudaStream_t s);
 size_t chain_smem_bytes(const Model &m, int warps_per_cta);
 int chain_max_warps_per_cta(const Model &m);
 

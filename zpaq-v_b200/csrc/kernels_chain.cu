@@ -24,6 +24,8 @@
 #include "common.cuh"
 #include "kernels.h"
 
+#include <type_traits>
+
 namespace zg {
 namespace {
 
@@ -122,6 +124,7 @@ struct Chain {
         h = 0, mix_h = 0;
         stage_mix();
     }
+
 
     __device__ void stage_mix() {
         if (MIX2) {
@@ -295,6 +298,298 @@ __device__ __forceinline__ u32 code_nibble(Chain<NI, MIX2> &C, u32 nib, u32 &c8,
     return got;
 }
 
+// ------------------------------------------------------------------------------------------
+// Tree decoder: the whole nibble is predicted speculatively, one lane per (tree node, outcome).
+//
+// The decoder cannot know bit k+1's context before bit k is decoded, but inside one nibble the
+// hash slot already holds the bit-history state of all 15 nodes of the nibble's binary context
+// tree.  Lane L owns node n = L & 15 and assumes outcome yy = L >> 4 for it.  In four lock-step
+// rounds (one per tree level) every lane evaluates the ICM/ISSE chain for its node from its own
+// view of the adaptive table entries and prepares the entry update its outcome would cause; the
+// update then reaches the descendants on that side of the node (one SHFL pair per component,
+// applied only where the descendant's state equals the ancestor's -- the only way a bit of the
+// nibble can influence a later one through the tables).  The arithmetic decoder then walks the
+// tree with one SHFL per bit and the nodes on the decoded path store their updates.  The serial
+// dependency per bit shrinks from "predict -> decode -> update -> next state -> predict" to the
+// decoder step itself; the rounds run ahead of it.  Results are bit-identical to the serial
+// evaluation (predictor.v:536-824): same table reads, same updates, in the same order.
+// ------------------------------------------------------------------------------------------
+template <int NI, bool MIX2>
+struct Tree {
+    static constexpr int NC = NI + 1;
+    const int16_t *stretch;
+    const u16 *squash;
+    const u16 *nex16;
+    int2 *tabs;        // NC tables of 256 entries: ICM {cm, stretch(cm>>8)}, ISSE {wt0, wt1}
+    u8 *slots;         // NC x 16 bytes: the hash slots of the current nibble
+    u16 *a16s;
+    u8 *ring;
+    u8 *stage;
+    // lanes 0..NI additionally own the hash table of component `lane`
+    u8 *ht;
+    u32 ht_len;
+    int sizebits;
+    u8 *slot_at;
+    const ModelDev *md;
+    u32 h;
+    bool owner;
+    u16 *a16;
+    u32 a16_mask, mix_h, mix_sel;
+    i32 mix_rate;
+    int ctx_mode, n_hash, n_comp;
+    u32 hist;
+    int lane;
+    // tree geometry of this lane
+    u32 node, yy;
+    int depth;
+    int src[3];        // lane whose prepared update reaches this node after round l (self when none does)
+
+    __device__ void setup(u8 *smem_warp, const ModelDev &M, u8 *ws, const int16_t *st, const u16 *sq,
+                          const u8 *nx) {
+        lane = threadIdx.x & 31;
+        owner = lane <= NI;
+        node = u32(lane) & 15u, yy = u32(lane) >> 4;
+        depth = 31 - __clz(int(node | 1u));
+#pragma unroll
+        for (int l = 0; l < 3; ++l) {
+            src[l] = lane;
+            if (l < depth) {
+                const u32 anc = node >> (depth - l), bit = (node >> (depth - l - 1)) & 1u;
+                src[l] = int(anc + 16u * bit);
+            }
+        }
+        stretch = st, squash = sq, nex16 = reinterpret_cast<const u16 *>(nx);
+        u8 *p = smem_warp;
+        tabs = reinterpret_cast<int2 *>(p);
+        p += size_t(NC) * 2048;
+        slots = p, p += 256;
+        a16s = reinterpret_cast<u16 *>(p), p += MIX2 ? 512 : 0;
+        ring = p, p += kRing;
+        stage = p;
+        ctx_mode = M.ctx_mode, n_hash = M.n_hash, n_comp = M.n;
+        const u32 *src0 = reinterpret_cast<const u32 *>(ws + M.comps[0].cm_off);
+        for (int k = lane; k < 256; k += 32) {
+            const u32 v = src0[k];
+            tabs[k] = make_int2(i32(v), i32(st[d_stretch_pad_idx(v >> 8)]));
+        }
+#pragma unroll
+        for (int i = 1; i <= NI; ++i) {
+            const int2 *srci = reinterpret_cast<const int2 *>(ws + M.comps[i].cm_off);
+            for (int k = lane; k < 256; k += 32) tabs[i * 256 + k] = srci[k];
+        }
+        for (int k = lane; k < 64; k += 32) reinterpret_cast<u32 *>(slots)[k] = 0;
+        ht = nullptr, ht_len = 16, sizebits = 0;
+        if (owner) {
+            const CompDesc &cd = M.comps[lane];
+            ht = ws + cd.ht_off, ht_len = cd.ht_len, sizebits = cd.a + 2;
+        }
+        slot_at = nullptr;
+        md = &M;
+        h = 0, hist = 0, mix_h = 0;
+        a16 = nullptr, a16_mask = 0, mix_sel = 0, mix_rate = 0;
+        if (MIX2) {
+            const CompDesc &cd = M.comps[NI + 1];
+            a16 = reinterpret_cast<u16 *>(ws + cd.a16_off);
+            a16_mask = cd.a16_len - 1, mix_sel = cd.p[3], mix_rate = i32(cd.p[2]);
+        }
+        __syncwarp();
+    }
+
+    __device__ void segment_reset() {
+        h = 0, mix_h = 0;
+        stage_mix();
+    }
+
+
+    __device__ void stage_mix() {
+        if (MIX2) {
+            __syncwarp();
+            for (int k = lane; k < 256; k += 32) a16s[k] = a16[(mix_h + u32(k)) & a16_mask];
+            __syncwarp();
+        }
+    }
+
+    __device__ __forceinline__ u32 ctx_next(u32 c, int sel, u32 &new_hist, u32 &mixv) const {
+        u32 mine = 0;
+        mixv = 0;
+        if (ctx_mode == CTX_M1) {
+            u32 a = (0u + c + 512u) * 773u;
+            a = (a + (hist & 255u) + 512u) * 773u;
+            const u32 h0 = a;
+            a = (a + ((hist >> 8) & 255u) + 512u) * 773u;
+            a = (a + ((hist >> 16) & 255u) + 512u) * 773u;
+            mine = sel == 0 ? h0 : (sel == 1 ? a : 0u);
+            new_hist = ((hist << 8) | c) & 0xFFFFFFu;
+        } else {
+            u32 a = c;
+            for (int r = 0; r < n_hash; ++r) {
+                a = (a + hist + 512u) * 773u;
+                if (r == sel) mine = a;
+                if (MIX2 && r == NI + 1) mixv = a;
+            }
+            new_hist = c;
+        }
+        return sel < n_comp ? mine : 0u;
+    }
+
+    __device__ void byte_end(u32 c) {
+        u32 nh, mixv;
+        h = ctx_next(c, lane, nh, mixv);
+        hist = nh;
+        if (MIX2) {
+            mix_h = mixv;
+            stage_mix();
+        }
+    }
+
+    // Predictor.find_ht for component `lane` (predictor.v:495-532); the chosen slot is published
+    // to the warp through shared memory.  The previous slot went back to HBM at the end of its nibble.
+    __device__ __forceinline__ void probe(u32 c8v) {
+        if (owner) {
+            const u32 key = h + 16u * c8v;
+            const u32 chk = (key >> sizebits) & 255u;
+            const u32 h0 = (key * 16u) & (ht_len - 16u);
+            u8 *b0 = ht_slot(*md, ht, h0);
+            u8 *b1 = reinterpret_cast<u8 *>(reinterpret_cast<uintptr_t>(b0) ^ 16u);
+            u8 *b2 = reinterpret_cast<u8 *>(reinterpret_cast<uintptr_t>(b0) ^ 32u);
+            const uint4 s0 = ldg128(b0), s1 = ldg128(b1), s2 = ldg128(b2);
+            const bool m0 = (s0.x & 255u) == chk, m1 = (s1.x & 255u) == chk, m2 = (s2.x & 255u) == chk;
+            const u32 q0 = (s0.x >> 8) & 255u, q1 = (s1.x >> 8) & 255u, q2 = (s2.x >> 8) & 255u;
+            u8 *victim = (q0 <= q1 && q0 <= q2) ? b0 : (q1 < q2 ? b1 : b2);
+            const bool hit = m0 | m1 | m2;
+            slot_at = m0 ? b0 : m1 ? b1 : m2 ? b2 : victim;
+            const uint4 pick = m0 ? s0 : (m1 ? s1 : s2);
+            uint4 sl;
+            sl.x = hit ? pick.x : chk;
+            sl.y = hit ? pick.y : 0u;
+            sl.z = hit ? pick.z : 0u;
+            sl.w = hit ? pick.w : 0u;
+            *reinterpret_cast<uint4 *>(slots + 16 * lane) = sl;
+        }
+        __syncwarp();
+    }
+};
+
+// Four bits of one nibble through the tree (see above).  c8 enters as 1 (high nibble) or 16..31.
+template <int NI, bool MIX2, class IO>
+__device__ __forceinline__ void decode_nibble_tree(Tree<NI, MIX2> &T, u32 &c8, u32 &low, u32 &high, u32 &code,
+                                                   IO &io) {
+    constexpr int NC = NI + 1;
+    const u32 node = T.node;
+    const int d = T.depth;
+    const i32 t = T.yy ? 32767 : 0;
+    // ---- this node's bit-history states and table entries (predictor.v:561, :622) ----
+    u32 st[NC], nx[NC];
+    int2 e[NC], u[NC];
+#pragma unroll
+    for (int c = 0; c < NC; ++c) st[c] = T.slots[c * 16 + node];
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+        e[c] = T.tabs[c * 256 + st[c]];
+        nx[c] = T.nex16[st[c]];
+    }
+    // where an ancestor's update lands on this node's entry: equal states, per component and level
+    u32 pk[2] = {0, 0};
+#pragma unroll
+    for (int c = 0; c < NC; ++c) pk[c >> 2] |= st[c] << (8 * (c & 3));
+    u32 eq[3][2];
+#pragma unroll
+    for (int l = 0; l < 3; ++l) {
+        const u32 anc = node >> max(d - l, 0);
+#pragma unroll
+        for (int w = 0; w < (NC + 3) / 4; ++w) {
+            const u32 a = __shfl_sync(kFull, pk[w], int(anc));
+            eq[l][w] = l < d ? __vcmpeq4(a, pk[w]) : 0u;
+        }
+    }
+    i32 mw = 0;
+    u32 msel = 0;
+    i32 nw = 0;
+    if (MIX2) {
+        msel = ((c8 << d) | (node - (1u << d))) & T.mix_sel;
+        mw = T.a16s[msel];
+    }
+    u32 idx = 1;
+    i32 sqf = 0;
+#pragma unroll
+    for (int l = 0; l < 4; ++l) {
+        // ---- predict this node from the current view of its entries (predictor.v:555-631) ----
+        i32 p[NC];
+        p[0] = e[0].y;
+#pragma unroll
+        for (int i = 1; i <= NI; ++i) p[i] = d_clamp2k((e[i].x * p[i - 1] + e[i].y * 64) >> 16);
+        i32 sq[NC];
+#pragma unroll
+        for (int i = 1; i <= NI; ++i) sq[i] = T.squash[p[i] + 2048];
+        if (MIX2) {
+            const i32 pf = d_clamp2k((mw * p[NI - 1] + (65536 - mw) * p[NI]) >> 16);
+            sqf = T.squash[pf + 2048];
+        } else {
+            sqf = NI > 0 ? sq[NI] : i32(T.squash[p[0] + 2048]);
+        }
+        // ---- decode the bit of tree level l: its node finished predicting in this round ----
+        const u32 p16 = u32(__shfl_sync(kFull, sqf, int(idx))) * 2u + 1u;
+        const u32 mid = coder_mid(low, high, p16);
+        const u32 y = code <= mid;
+        if (y) high = mid; else low = mid + 1;
+        // ---- the update outcome yy would cause (predictor.v:701-709, :776-791, :744-762) ----
+        {
+            const u32 v0 = u32(e[0].x);
+            const u32 v = u32(i32(v0) + ((t - i32(v0 >> 8)) >> 2));
+            u[0] = make_int2(i32(v), i32(T.stretch[d_stretch_pad_idx(v >> 8)]));
+        }
+#pragma unroll
+        for (int i = 1; i <= NI; ++i) {
+            const i32 err = t - sq[i];
+            u[i] = make_int2(d_clamp512k(e[i].x + ((err * p[i - 1] + 4096) >> 13)),
+                             d_clamp512k(e[i].y + ((err + 16) >> 5)));
+        }
+        if (MIX2) {
+            const i32 merr = ((t - sqf) * T.mix_rate) >> 5;
+            nw = max(0, min(65535, mw + ((merr * (p[NI - 1] - p[NI]) + 4096) >> 13)));
+        }
+        // ---- hand the update down the side of the tree that outcome leads to ----
+        if (l < 3) {
+#pragma unroll
+            for (int c = 0; c < NC; ++c) {
+                const i32 fx = __shfl_sync(kFull, u[c].x, T.src[l]);
+                const i32 fy = __shfl_sync(kFull, u[c].y, T.src[l]);
+                if ((eq[l][c >> 2] >> (8 * (c & 3))) & 1u) e[c] = make_int2(fx, fy);
+            }
+        }
+        // ---- decoder renormalisation (decoder.v:104-117) ----
+        while ((high ^ low) < 0x1000000u) {
+            low <<= 8;
+            high = (high << 8) | 0xFFu;
+            if (low == 0) low = 1;
+            code = (code << 8) | io.get();
+        }
+        idx = idx * 2 + y;
+    }
+    // ---- the nodes on the decoded path learn: table entries, successor states ----
+    const u32 full = idx;  // 16 + the four bits
+    const bool mine = node != 0 && (full >> (4 - d)) == node && ((full >> (3 - d)) & 1u) == T.yy;
+#pragma unroll
+    for (int l = 0; l < 4; ++l) {  // level order: a deeper node with the same state holds the later value
+        if (mine && d == l) {
+#pragma unroll
+            for (int c = 0; c < NC; ++c) T.tabs[c * 256 + st[c]] = u[c];
+        }
+        __syncwarp();
+    }
+    if (mine) {
+#pragma unroll
+        for (int c = 0; c < NC; ++c) T.slots[c * 16 + node] = u8((nx[c] >> (T.yy * 8u)) & 255u);
+        if (MIX2) {
+            T.a16s[msel] = u16(nw);
+            T.a16[(T.mix_h + msel) & T.a16_mask] = u16(nw);
+        }
+    }
+    __syncwarp();
+    if (T.owner) *reinterpret_cast<uint4 *>(T.slot_at) = *reinterpret_cast<const uint4 *>(T.slots + 16 * T.lane);
+    c8 = (c8 << 4) | (full & 15u);
+}
+
 // ---- byte I/O over the shared-memory stages (all lanes execute, same address) ----
 struct DecIO {
     const u8 *ring;
@@ -336,7 +631,7 @@ __device__ __forceinline__ void load_shared_tables(u8 *smem, const DevTables &T)
 // ------------------------------------------------------------------------------------------
 // k_decode_chain
 // ------------------------------------------------------------------------------------------
-template <int NI, bool MIX2>
+template <int NI, bool MIX2, bool TREE>
 __global__ void __launch_bounds__(256, 1) k_decode_chain(DecodeArgs A) {
     extern __shared__ __align__(16) u8 smem[];
     load_shared_tables(smem, A.tables);
@@ -344,7 +639,7 @@ __global__ void __launch_bounds__(256, 1) k_decode_chain(DecodeArgs A) {
     const int slot = blockIdx.x * (blockDim.x >> 5) + wic;
     if (slot >= A.n_blocks) return;
     const int bi = A.first_block + slot;
-    Chain<NI, MIX2> C;
+    typename std::conditional<TREE, Tree<NI, MIX2>, Chain<NI, MIX2>>::type C;
     u8 *ws = A.workspace + u64(slot) * A.model.ws_bytes;
     C.setup(smem + kSharedTables + size_t(wic) * warp_smem_bytes(NI, MIX2), A.model, ws,
             reinterpret_cast<const int16_t *>(smem), reinterpret_cast<const u16 *>(smem + 65536),
@@ -402,7 +697,8 @@ __global__ void __launch_bounds__(256, 1) k_decode_chain(DecodeArgs A) {
 #pragma unroll 1
             for (int half = 0; half < 2; ++half) {
                 C.probe(c8);
-                code_nibble<NI, MIX2, true>(C, 0, c8, low, high, code, io);
+                if constexpr (TREE) decode_nibble_tree<NI, MIX2>(C, c8, low, high, code, io);
+                else code_nibble<NI, MIX2, true>(C, 0, c8, low, high, code, io);
             }
             const u32 ch = c8 & 255u;
             C.byte_end(ch);
@@ -479,20 +775,24 @@ int chain_max_warps_per_cta(const Model &m) {
     return w > 8 ? 8 : w;
 }
 
-template <int NI, bool MIX2>
+template <int NI, bool MIX2, bool TREE>
 static bool launch_dec(const DecodeArgs &D, int wpc, size_t smem, cudaStream_t s) {
     const int grid = (D.n_blocks + wpc - 1) / wpc;
-    auto k = k_decode_chain<NI, MIX2>;
+    auto k = k_decode_chain<NI, MIX2, TREE>;
     if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)) != cudaSuccess) return false;
     k<<<grid, wpc * 32, smem, s>>>(D);
     return true;
 }
 
-bool launch_decode_chain(const Model &m, const DecodeArgs &A, int wpc, cudaStream_t s) {
+bool launch_decode_chain(const Model &m, const DecodeArgs &A, int wpc, bool tree, cudaStream_t s) {
     if (!m.is_chain) return false;
     const size_t smem = chain_smem_bytes(m, wpc);
-#define ZG_CASE(NI, MX) \
-    if (m.n_isse == NI && m.has_mix2 == MX) return launch_dec<NI, MX>(A, wpc, smem, s);
+    // the tree decoder takes MIX2 weights per node from the staged copy: that needs every c8 of a byte
+    // to select its own weight (mask 255, as -m4/-m5 have); other masks keep the serial decoder
+    if (m.has_mix2 && m.comps[size_t(m.n_isse) + 1].p[3] != 255) tree = false;
+#define ZG_CASE(NI, MX)                                                        \
+    if (m.n_isse == NI && m.has_mix2 == MX)                                    \
+        return tree ? launch_dec<NI, MX, true>(A, wpc, smem, s) : launch_dec<NI, MX, false>(A, wpc, smem, s);
     ZG_CASE(0, false) ZG_CASE(1, false) ZG_CASE(2, false) ZG_CASE(3, false) ZG_CASE(4, false)
     ZG_CASE(5, false) ZG_CASE(6, false) ZG_CASE(7, false)
     ZG_CASE(2, true) ZG_CASE(3, true) ZG_CASE(4, true) ZG_CASE(5, true) ZG_CASE(6, true) ZG_CASE(7, true)
