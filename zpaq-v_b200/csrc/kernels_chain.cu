@@ -343,6 +343,10 @@ struct Tree {
     u32 node, yy;
     int depth;
     int src[3];        // lane whose prepared update reaches this node after round l (self when none does)
+    // candidate slots of the NEXT nibble, requested as soon as its context is known (probe_issue)
+    uint4 q0, q1, q2;
+    u8 *qb0;
+    bool q_ok;
 
     __device__ void setup(u8 *smem_warp, const ModelDev &M, u8 *ws, const int16_t *st, const u16 *sq,
                           const u8 *nx) {
@@ -386,6 +390,8 @@ struct Tree {
         slot_at = nullptr;
         md = &M;
         h = 0, hist = 0, mix_h = 0;
+        q_ok = false, qb0 = nullptr;
+        q0 = q1 = q2 = make_uint4(0, 0, 0, 0);
         a16 = nullptr, a16_mask = 0, mix_sel = 0, mix_rate = 0;
         if (MIX2) {
             const CompDesc &cd = M.comps[NI + 1];
@@ -397,7 +403,34 @@ struct Tree {
 
     __device__ void segment_reset() {
         h = 0, mix_h = 0;
+        q_ok = false;  // requested with the old contexts
         stage_mix();
+    }
+
+    // Called as soon as the four bits of a nibble are decoded (c8new = c8 after them): the owners
+    // request the three candidate slots of the following nibble right away, so that the HBM/L2 round
+    // trip runs under the table updates, the slot write-back and the per-byte bookkeeping instead of
+    // after them.  Loads only; the choice (and any eviction) happens in probe().  A line that is the
+    // current slot's own line is not requested early: it changes at the write-back.
+    __device__ __forceinline__ void probe_issue(u32 c8new) {
+        q_ok = false;
+        if (owner) {
+            u32 key;
+            if (c8new < 256u) {
+                key = h + 16u * c8new;              // low nibble of the same byte
+            } else {
+                u32 nh, mixv;                       // high nibble of the next byte (predictor.v:809-818)
+                key = ctx_next(c8new & 255u, lane, nh, mixv) + 16u;
+            }
+            u8 *b0 = ht_slot(*md, ht, (key * 16u) & (ht_len - 16u));
+            if (((reinterpret_cast<uintptr_t>(b0) ^ reinterpret_cast<uintptr_t>(slot_at)) & ~uintptr_t(63)) != 0) {
+                qb0 = b0;
+                q0 = ldg128(b0);
+                q1 = ldg128(reinterpret_cast<u8 *>(reinterpret_cast<uintptr_t>(b0) ^ 16u));
+                q2 = ldg128(reinterpret_cast<u8 *>(reinterpret_cast<uintptr_t>(b0) ^ 32u));
+                q_ok = true;
+            }
+        }
     }
 
 
@@ -448,14 +481,21 @@ struct Tree {
         if (owner) {
             const u32 key = h + 16u * c8v;
             const u32 chk = (key >> sizebits) & 255u;
-            const u32 h0 = (key * 16u) & (ht_len - 16u);
-            u8 *b0 = ht_slot(*md, ht, h0);
+            u8 *b0 = qb0;
+            uint4 s0 = q0, s1 = q1, s2 = q2;
+            if (!q_ok) {
+                b0 = ht_slot(*md, ht, (key * 16u) & (ht_len - 16u));
+                asm volatile("" ::: "memory");  // after the write-back of the previous slot
+                s0 = ldg128(b0);
+                s1 = ldg128(reinterpret_cast<u8 *>(reinterpret_cast<uintptr_t>(b0) ^ 16u));
+                s2 = ldg128(reinterpret_cast<u8 *>(reinterpret_cast<uintptr_t>(b0) ^ 32u));
+            }
+            q_ok = false;
             u8 *b1 = reinterpret_cast<u8 *>(reinterpret_cast<uintptr_t>(b0) ^ 16u);
             u8 *b2 = reinterpret_cast<u8 *>(reinterpret_cast<uintptr_t>(b0) ^ 32u);
-            const uint4 s0 = ldg128(b0), s1 = ldg128(b1), s2 = ldg128(b2);
             const bool m0 = (s0.x & 255u) == chk, m1 = (s1.x & 255u) == chk, m2 = (s2.x & 255u) == chk;
-            const u32 q0 = (s0.x >> 8) & 255u, q1 = (s1.x >> 8) & 255u, q2 = (s2.x >> 8) & 255u;
-            u8 *victim = (q0 <= q1 && q0 <= q2) ? b0 : (q1 < q2 ? b1 : b2);
+            const u32 p0 = (s0.x >> 8) & 255u, p1 = (s1.x >> 8) & 255u, p2 = (s2.x >> 8) & 255u;
+            u8 *victim = (p0 <= p1 && p0 <= p2) ? b0 : (p1 < p2 ? b1 : b2);
             const bool hit = m0 | m1 | m2;
             slot_at = m0 ? b0 : m1 ? b1 : m2 ? b2 : victim;
             const uint4 pick = m0 ? s0 : (m1 ? s1 : s2);
@@ -566,8 +606,9 @@ __device__ __forceinline__ void decode_nibble_tree(Tree<NI, MIX2> &T, u32 &c8, u
         }
         idx = idx * 2 + y;
     }
-    // ---- the nodes on the decoded path learn: table entries, successor states ----
     const u32 full = idx;  // 16 + the four bits
+    T.probe_issue((c8 << 4) | (full & 15u));
+    // ---- the nodes on the decoded path learn: table entries, successor states ----
     const bool mine = node != 0 && (full >> (4 - d)) == node && ((full >> (3 - d)) & 1u) == T.yy;
 #pragma unroll
     for (int l = 0; l < 4; ++l) {  // level order: a deeper node with the same state holds the later value
