@@ -554,6 +554,7 @@ int run_decompress(zpaqgpu_ctx *ctx, DecompressJob &job, bool caller_owns_plain)
                             da.seg_recs = static_cast<DecSegRec *>(ctx->seg_recs.p);
                             da.seg_count = static_cast<u32 *>(ctx->misc.p);
                             da.seg_cap = seg_cap, da.first_block = first, da.n_blocks = cnt;
+                            da.flags = ctx->spec_probe ? 1 : 0;
                             CK(cudaEventRecord(ctx->ev[0], st));
                             if (store) {
                                 da.model = mod.dense;
@@ -727,6 +728,7 @@ int zpaqgpu_init(zpaqgpu_ctx **out, int device) {
     zpaqgpu_ctx *ctx = new zpaqgpu_ctx();
     ctx->device = device;
     if (const char *v = std::getenv("ZPAQGPU_DECODER")) ctx->tree_decoder = std::strcmp(v, "serial") != 0;
+    if (const char *v = std::getenv("ZPAQGPU_SPEC_PROBE")) ctx->spec_probe = std::atoi(v) != 0;
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->sm_count = prop.multiProcessorCount;
     bool ok = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) == cudaSuccess &&

@@ -33,6 +33,7 @@ struct DecodeArgs {
     u32 seg_cap;
     int first_block;
     int n_blocks;
+    int flags;               // tree decoder: 1 = request the next nibble's candidate slots two bits early
 };
 
 // generic (all nine component types, ZPAQL interpreter)

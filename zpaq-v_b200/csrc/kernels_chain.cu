@@ -325,14 +325,17 @@ struct Tree {
     u16 *a16s;
     u8 *ring;
     u8 *stage;
-    // lanes 0..NI additionally own the hash table of component `lane`
+    // Probing role: lane = (component pc = lane & 7, candidate pcand = lane >> 3).  The four lanes of a
+    // component hold its table geometry, context hash and current slot address; see probe_issue().
     u8 *ht;
     u32 ht_len;
     int sizebits;
     u8 *slot_at;
     const ModelDev *md;
     u32 h;
-    bool owner;
+    bool owner;        // pc < NC
+    int pc;
+    u32 pcand;
     u16 *a16;
     u32 a16_mask, mix_h, mix_sel;
     i32 mix_rate;
@@ -343,15 +346,17 @@ struct Tree {
     u32 node, yy;
     int depth;
     int src[3];        // lane whose prepared update reaches this node after round l (self when none does)
-    // candidate slots of the NEXT nibble, requested as soon as its context is known (probe_issue)
+    // candidate slots of the NEXT nibble, requested two bits before its context is known
     uint4 q0, q1, q2;
     u8 *qb0;
-    bool q_ok;
+    u32 q_key, cur_vline;   // cur_vline: 64-byte line (virtual offset >> 6) of the current slot
+    bool q_ok, actor, spec;
 
     __device__ void setup(u8 *smem_warp, const ModelDev &M, u8 *ws, const int16_t *st, const u16 *sq,
                           const u8 *nx) {
         lane = threadIdx.x & 31;
-        owner = lane <= NI;
+        pc = lane & 7, pcand = u32(lane) >> 3;
+        owner = pc <= NI;
         node = u32(lane) & 15u, yy = u32(lane) >> 4;
         depth = 31 - __clz(int(node | 1u));
 #pragma unroll
@@ -384,13 +389,13 @@ struct Tree {
         for (int k = lane; k < 64; k += 32) reinterpret_cast<u32 *>(slots)[k] = 0;
         ht = nullptr, ht_len = 16, sizebits = 0;
         if (owner) {
-            const CompDesc &cd = M.comps[lane];
+            const CompDesc &cd = M.comps[pc];
             ht = ws + cd.ht_off, ht_len = cd.ht_len, sizebits = cd.a + 2;
         }
         slot_at = nullptr;
         md = &M;
         h = 0, hist = 0, mix_h = 0;
-        q_ok = false, qb0 = nullptr;
+        q_ok = false, qb0 = nullptr, q_key = 0, cur_vline = ~0u, actor = false, spec = true;
         q0 = q1 = q2 = make_uint4(0, 0, 0, 0);
         a16 = nullptr, a16_mask = 0, mix_sel = 0, mix_rate = 0;
         if (MIX2) {
@@ -407,23 +412,32 @@ struct Tree {
         stage_mix();
     }
 
-    // Called as soon as the four bits of a nibble are decoded (c8new = c8 after them): the owners
-    // request the three candidate slots of the following nibble right away, so that the HBM/L2 round
-    // trip runs under the table updates, the slot write-back and the per-byte bookkeeping instead of
-    // after them.  Loads only; the choice (and any eviction) happens in probe().  A line that is the
-    // current slot's own line is not requested early: it changes at the write-back.
-    __device__ __forceinline__ void probe_issue(u32 c8new) {
+    // Address of a slot without side effects: nullptr when a paged table has no page there yet.
+    __device__ __forceinline__ u8 *slot_peek(u32 h0) const {
+        if (!md->paged) return ht + h0;
+        const u32 pte = reinterpret_cast<const u32 *>(ht)[h0 / kPageBytes];
+        return pte ? md->pool + u64(pte - 1u) * kPageBytes + (h0 & (kPageBytes - 1u)) : nullptr;
+    }
+
+    // Called when the first two bits of a nibble are decoded (c8part = c8 after them).  The slot the
+    // NEXT nibble probes is then one of four; lane (pc, pcand) requests the three candidate slots of
+    // the line its completion pcand would lead to, so the HBM/L2 round trip runs under the remaining
+    // two tree rounds, the table updates and the per-byte bookkeeping instead of after them.  Loads
+    // only: the choice (and any eviction) happens in probe().  A line that is the current slot's own
+    // line is not requested: it changes at the write-back.
+    __device__ __forceinline__ void probe_issue(u32 c8part) {
         q_ok = false;
-        if (owner) {
-            u32 key;
+        if (owner && spec) {
+            const u32 c8new = (c8part << 2) | pcand;
             if (c8new < 256u) {
-                key = h + 16u * c8new;              // low nibble of the same byte
+                q_key = h + 16u * c8new;            // low nibble of the same byte
             } else {
                 u32 nh, mixv;                       // high nibble of the next byte (predictor.v:809-818)
-                key = ctx_next(c8new & 255u, lane, nh, mixv) + 16u;
+                q_key = ctx_next(c8new & 255u, pc, nh, mixv) + 16u;
             }
-            u8 *b0 = ht_slot(*md, ht, (key * 16u) & (ht_len - 16u));
-            if (((reinterpret_cast<uintptr_t>(b0) ^ reinterpret_cast<uintptr_t>(slot_at)) & ~uintptr_t(63)) != 0) {
+            const u32 h0 = (q_key * 16u) & (ht_len - 16u);
+            u8 *b0 = slot_peek(h0);
+            if (b0 && (h0 >> 6) != cur_vline) {
                 qb0 = b0;
                 q0 = ldg128(b0);
                 q1 = ldg128(reinterpret_cast<u8 *>(reinterpret_cast<uintptr_t>(b0) ^ 16u));
@@ -432,7 +446,6 @@ struct Tree {
             }
         }
     }
-
 
     __device__ void stage_mix() {
         if (MIX2) {
@@ -467,7 +480,7 @@ struct Tree {
 
     __device__ void byte_end(u32 c) {
         u32 nh, mixv;
-        h = ctx_next(c, lane, nh, mixv);
+        h = ctx_next(c, pc, nh, mixv);
         hist = nh;
         if (MIX2) {
             mix_h = mixv;
@@ -475,22 +488,28 @@ struct Tree {
         }
     }
 
-    // Predictor.find_ht for component `lane` (predictor.v:495-532); the chosen slot is published
-    // to the warp through shared memory.  The previous slot went back to HBM at the end of its nibble.
+    // Predictor.find_ht of every component (predictor.v:495-532).  For each component the lane whose
+    // early request turned out to be the right one makes the choice from its registers; when there is
+    // none (first nibble of a segment, own-line hazard, unmapped page) candidate lane 0 loads now.
+    // The chosen slot and its address are published to the warp through shared memory.
     __device__ __forceinline__ void probe(u32 c8v) {
-        if (owner) {
-            const u32 key = h + 16u * c8v;
+        const u32 key = h + 16u * c8v;
+        const bool match = owner && q_ok && q_key == key;
+        const u32 grp = (__ballot_sync(kFull, match) >> pc) & 0x01010101u;
+        actor = owner && (grp ? match : pcand == 0u);
+        const u32 h0 = (key * 16u) & (ht_len - 16u);
+        cur_vline = h0 >> 6;
+        if (actor) {
             const u32 chk = (key >> sizebits) & 255u;
             u8 *b0 = qb0;
             uint4 s0 = q0, s1 = q1, s2 = q2;
-            if (!q_ok) {
-                b0 = ht_slot(*md, ht, (key * 16u) & (ht_len - 16u));
+            if (!match) {
+                b0 = ht_slot(*md, ht, h0);
                 asm volatile("" ::: "memory");  // after the write-back of the previous slot
                 s0 = ldg128(b0);
                 s1 = ldg128(reinterpret_cast<u8 *>(reinterpret_cast<uintptr_t>(b0) ^ 16u));
                 s2 = ldg128(reinterpret_cast<u8 *>(reinterpret_cast<uintptr_t>(b0) ^ 32u));
             }
-            q_ok = false;
             u8 *b1 = reinterpret_cast<u8 *>(reinterpret_cast<uintptr_t>(b0) ^ 16u);
             u8 *b2 = reinterpret_cast<u8 *>(reinterpret_cast<uintptr_t>(b0) ^ 32u);
             const bool m0 = (s0.x & 255u) == chk, m1 = (s1.x & 255u) == chk, m2 = (s2.x & 255u) == chk;
@@ -504,8 +523,9 @@ struct Tree {
             sl.y = hit ? pick.y : 0u;
             sl.z = hit ? pick.z : 0u;
             sl.w = hit ? pick.w : 0u;
-            *reinterpret_cast<uint4 *>(slots + 16 * lane) = sl;
+            *reinterpret_cast<uint4 *>(slots + 16 * pc) = sl;
         }
+        q_ok = false;
         __syncwarp();
     }
 };
@@ -605,9 +625,9 @@ __device__ __forceinline__ void decode_nibble_tree(Tree<NI, MIX2> &T, u32 &c8, u
             code = (code << 8) | io.get();
         }
         idx = idx * 2 + y;
+        if (l == 1) T.probe_issue((c8 << 2) | (idx & 3u));
     }
     const u32 full = idx;  // 16 + the four bits
-    T.probe_issue((c8 << 4) | (full & 15u));
     // ---- the nodes on the decoded path learn: table entries, successor states ----
     const bool mine = node != 0 && (full >> (4 - d)) == node && ((full >> (3 - d)) & 1u) == T.yy;
 #pragma unroll
@@ -627,7 +647,7 @@ __device__ __forceinline__ void decode_nibble_tree(Tree<NI, MIX2> &T, u32 &c8, u
         }
     }
     __syncwarp();
-    if (T.owner) *reinterpret_cast<uint4 *>(T.slot_at) = *reinterpret_cast<const uint4 *>(T.slots + 16 * T.lane);
+    if (T.actor) *reinterpret_cast<uint4 *>(T.slot_at) = *reinterpret_cast<const uint4 *>(T.slots + 16 * T.pc);
     c8 = (c8 << 4) | (full & 15u);
 }
 
@@ -685,6 +705,7 @@ __global__ void __launch_bounds__(256, 1) k_decode_chain(DecodeArgs A) {
     C.setup(smem + kSharedTables + size_t(wic) * warp_smem_bytes(NI, MIX2), A.model, ws,
             reinterpret_cast<const int16_t *>(smem), reinterpret_cast<const u16 *>(smem + 65536),
             smem + 65536 + 8192);
+    if constexpr (TREE) C.spec = A.flags != 0;
     const DecBlock blk = A.blocks[bi];
     const u8 *arc = A.arc;
     u64 pos = blk.arc_pos;  // uniform across the warp
