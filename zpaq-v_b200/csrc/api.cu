@@ -318,6 +318,7 @@ int run_compress(zpaqgpu_ctx *ctx, CompressJob &job) {
                     ea.in = job.d_in, ea.arena = static_cast<u8 *>(ctx->arena.p);
                     ea.blocks = d_blocks, ea.segs = d_esegs, ea.pay_len = static_cast<u64 *>(ctx->pay_len.p);
                     ea.first_block = first, ea.n_blocks = n;
+                    ea.flags = std::getenv("ZPAQGPU_ENC_FLAGS") ? std::atoi(std::getenv("ZPAQGPU_ENC_FLAGS")) : 1;
                     if (chain) {
                         if (!launch_encode_pipe3(m, ea, wpc, st)) {
                             ctx->err = "no chain kernel instantiation for this model";

@@ -17,6 +17,7 @@ struct EncodeArgs {
     u64 *pay_len;            // per segment: coded payload bytes (counted even past pay_cap)
     int first_block;         // wave offset into blocks[]
     int n_blocks;            // blocks in this wave
+    int flags;               // 1: the history warp pulls the next nibble's slot line into L1 one step early
 };
 
 struct DecodeArgs {
