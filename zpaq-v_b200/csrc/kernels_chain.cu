@@ -849,9 +849,11 @@ static bool launch_dec(const DecodeArgs &D, int wpc, size_t smem, cudaStream_t s
 bool launch_decode_chain(const Model &m, const DecodeArgs &A, int wpc, bool tree, cudaStream_t s) {
     if (!m.is_chain) return false;
     const size_t smem = chain_smem_bytes(m, wpc);
-    // the tree decoder takes MIX2 weights per node from the staged copy: that needs every c8 of a byte
-    // to select its own weight (mask 255, as -m4/-m5 have); other masks keep the serial decoder
-    if (m.has_mix2 && m.comps[size_t(m.n_isse) + 1].p[3] != 255) tree = false;
+    // The tree decoder evaluates all components of a node in one lane, the serial decoder spreads the
+    // components over lanes: measured on B200 (512 x 128 KiB text) the tree wins at -m1/-m2/-m3
+    // (-16/-15/-11 % kernel time) and loses at -m4/-m5 (six and eight components plus MIX2, +33/+30 %).
+    // It also takes MIX2 weights per node from the staged copy, which needs mask 255.
+    if (m.has_mix2 || m.n_isse > 4) tree = false;
 #define ZG_CASE(NI, MX)                                                        \
     if (m.n_isse == NI && m.has_mix2 == MX)                                    \
         return tree ? launch_dec<NI, MX, true>(A, wpc, smem, s) : launch_dec<NI, MX, false>(A, wpc, smem, s);
