@@ -360,8 +360,12 @@ def main():
     n_ht = N_HT.get(level, 3)
     # algorithmic bytes per input byte the codec kernel asks of the memory system:
     # plaintext (1) + coded bytes (ratio) + per nibble and hash-table component one 64-byte probe line
-    # read and one 16-byte slot write-back (2 nibbles per byte)
-    alg_per_byte = 1.0 + ratio + 2 * n_ht * (64 + 16)
+    # read and one 16-byte slot write-back (2 nibbles per byte).  The tree decoder (-m1..-m3) requests
+    # the four possible lines of the next nibble two bits early: four line reads per probe instead of one.
+    tree_dec = level <= 3 and os.environ.get("ZPAQGPU_DECODER", "tree") != "serial"
+    spec = 4 if (tree_dec and os.environ.get("ZPAQGPU_SPEC_PROBE", "1") != "0") else 1
+    alg_enc = 1.0 + ratio + 2 * n_ht * (64 + 16)
+    alg_dec = 1.0 + ratio + 2 * n_ht * (64 * spec + 16)
     enc_ms = kern_ms["enc"] / max(1, kern_ms["enc_n"])
     dec_ms = kern_ms["dec"] / max(1, kern_ms["dec_n"])
     launch_bytes = total / max(1, st_d["waves"])
@@ -376,19 +380,20 @@ def main():
     except Exception:
         pass
 
-    def roof(ms, name, key):
-        ach = launch_bytes * alg_per_byte / (ms / 1e3) / 1e9
+    def roof(ms, name, key, alg):
+        ach = launch_bytes * alg / (ms / 1e3) / 1e9
         return {"kernel": name, "achieved": round(ach, 2), "frac": round(ach / hbm_peak, 5), "kernel_ms": round(ms, 3),
-                "traffic": traffic[key],
+                "traffic": traffic[key], "algorithmic_bytes_per_input_byte": round(alg, 2),
                 "issue_frac": round(launch_bytes / (ms / 1e3) * W_OPS.get(level, 0) / issue_peak, 5)}
 
-    tag = "%d,%s" % (N_HT.get(level, 3) - 1 - (1 if level >= 4 else 0) + (0), "true" if level >= 4 else "false")
-    dec_r = roof(dec_ms, "k_decode_chain<%s>" % tag, "decode")
-    enc_r = roof(enc_ms, "k_encode_pipe3<%s>" % tag, "encode")
+    n_isse = N_HT.get(level, 3) - 1
+    mix = "true" if level >= 4 else "false"
+    dec_r = roof(dec_ms, "k_decode_chain<%d,%s,%s>" % (n_isse, mix, "true" if tree_dec else "false"), "decode", alg_dec)
+    enc_r = roof(enc_ms, "k_encode_pipe3<%d,%s>" % (n_isse, mix), "encode", alg_enc)
     roofline = {
         "bound": "hbm", "kernel": dec_r["kernel"], "achieved": dec_r["achieved"], "peak": hbm_peak, "unit": "GB/s",
         "frac": dec_r["frac"], "peak_source": peak_kind, "traffic": dec_r["traffic"],
-        "algorithmic_bytes_per_input_byte": round(alg_per_byte, 2), "units_per_launch": int(launch_bytes),
+        "algorithmic_bytes_per_input_byte": dec_r["algorithmic_bytes_per_input_byte"], "units_per_launch": int(launch_bytes),
         "kernel_ms": dec_r["kernel_ms"], "encode": enc_r,
         "note": "bit-serial integer chain: the binding limit is the dependent-instruction latency of one warp per "
                 "block, not HBM; issue_roofline = W(L) ops/byte x bytes/s / (148 SM x 128 lanes x f_clk)",

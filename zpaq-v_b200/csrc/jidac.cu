@@ -26,7 +26,7 @@ using namespace zg;
 namespace zg {
 namespace {
 
-constexpr int kFragThreads = 64;
+constexpr int kFragThreads = 32;  // one warp per CTA: the prediction tables take 8 KiB of shared memory
 constexpr u32 kEmpty = 0xFFFFFFFFu;
 
 struct FragArgs {
@@ -49,7 +49,8 @@ struct FragArgs {
 // 64<<fragment bytes.  h, c1 and o1 start from zero in every fragment, which makes the fragments of
 // one file a serial chain; parallelism is across files.
 __global__ void __launch_bounds__(kFragThreads) k_fragment_files(FragArgs A) {
-    __shared__ u8 o1[256 * kFragThreads];
+    // o1[c1] of lane t lives in byte (c1 & 3) of word (c1 >> 2) * 32 + t: every lane has its own bank
+    __shared__ u32 o1w[64 * kFragThreads];
     const int t = blockIdx.x * kFragThreads + threadIdx.x;
     if (t >= A.n_files) return;
     const u32 f = A.order[t];
@@ -63,24 +64,52 @@ __global__ void __launch_bounds__(kFragThreads) k_fragment_files(FragArgs A) {
     const u64 minf = 64ull << A.fragment, maxf = 8128ull << A.fragment;
     const bool hashed = A.fragment <= 22;
     const u32 thresh = hashed ? (1u << (22 - A.fragment)) : 0u;
-    u8 *mine = o1 + threadIdx.x;
-    const u8 *in = A.in;
+    u8 *mine = reinterpret_cast<u8 *>(o1w) + 4 * threadIdx.x;
+    auto slot = [&](u32 c1) -> u8 * { return mine + (c1 >> 2) * (4 * kFragThreads) + (c1 & 3u); };
+    const u8 *in = A.in;  // 16-byte aligned; the buffer has slack past the last byte
     u32 cnt = 0;
     u64 pos = lo;
-    while (pos < hi) {
-        for (int k = 0; k < 256; ++k) mine[k * kFragThreads] = 0;
-        u32 h = 0, c1 = 0;
-        const u64 stop = min(hi, pos + maxf), earliest = pos + minf;
-        while (pos < stop) {
-            const u32 c = __ldg(in + pos);
-            ++pos;
-            const u32 pred = mine[c1 * kFragThreads];
-            h = (h + c + 1u) * (c == pred ? 314159265u : 271828182u);
-            mine[c1 * kFragThreads] = u8(c);
-            c1 = c;
-            if (hashed && h < thresh && pos >= earliest) break;
+    // One flat loop, one aligned 16-byte piece per step and lane (the next piece is requested before
+    // this one is walked), so that the lanes of a warp -- files of similar length -- stay converged.
+    // All bytes of a piece are hashed without looking at the cut condition: what the table and h hold
+    // after a cut is thrown away by the reset that follows, and this keeps the table accesses and the
+    // multiply chain free of the compare.
+    uint4 nxt = *reinterpret_cast<const uint4 *>(in + (pos & ~15ull));
+    for (int k = 0; k < 64; ++k) o1w[k * kFragThreads + threadIdx.x] = 0;
+    u32 h = 0, c1 = 0;
+    u64 stop = min(hi, pos + maxf), earliest = pos + minf;
+    bool active = pos < hi;
+    while (active) {
+        const u64 base = pos & ~15ull;
+        const uint4 v = nxt;
+        nxt = *reinterpret_cast<const uint4 *>(in + base + 16);
+        const u32 w4[4] = {v.x, v.y, v.z, v.w};
+        const u32 j0 = u32(pos - base);
+        const u32 j1 = stop - base < 16 ? u32(stop - base) : 16u;  // bytes of this piece inside the fragment limit
+        const u32 je = earliest > base ? (earliest - base < 64 ? u32(earliest - base) : 64u) : 0u;
+        u32 first_cut = 32;
+#pragma unroll
+        for (u32 j = 0; j < 16; ++j) {
+            if (j >= j0) {
+                const u32 c = (w4[j >> 2] >> (8 * (j & 3))) & 255u;
+                u8 *at = slot(c1);
+                const u32 pred = *at;
+                h = (h + c + 1u) * (c == pred ? 314159265u : 271828182u);
+                *at = u8(c);
+                c1 = c;
+                if (hashed && h < thresh && j + 1 >= je) first_cut = min(first_cut, j + 1);
+            }
         }
-        ends[cnt++] = pos;
+        const u32 upto = min(first_cut, j1);  // first_cut beyond j1 lies past the size limit / end of file
+        pos = base + upto;
+        if (first_cut <= j1 || pos >= stop) {  // the fragment ends here
+            ends[cnt++] = pos;
+            for (int k = 0; k < 64; ++k) o1w[k * kFragThreads + threadIdx.x] = 0;
+            h = 0, c1 = 0;
+            stop = min(hi, pos + maxf), earliest = pos + minf;
+            active = pos < hi;
+            if ((pos & 15ull) != 0) nxt = v;  // the next fragment starts inside this piece
+        }
     }
     A.count[f] = cnt;
 }
@@ -270,7 +299,7 @@ int jidac_front(zpaqgpu_ctx *ctx, const uint8_t *in, const uint64_t *in_off, int
     S.input_bytes = R.total_in;
     if (R.total_in && !in) return ZPAQGPU_E_ARG;
     int rc;
-    if ((rc = ensure(ctx, ctx->jd_in, std::max<u64>(R.total_in, 16)))) return rc;
+    if ((rc = ensure(ctx, ctx->jd_in, R.total_in + 64))) return rc;  // k_fragment_files reads whole 16-byte pieces
     Timer t_h2d, t_frag, t_sha, t_dedup, t_gather;
     t_h2d.start(st);
     if (R.total_in) CK(cudaMemcpyAsync(ctx->jd_in.p, in + base, R.total_in, cudaMemcpyHostToDevice, st));
