@@ -253,7 +253,8 @@ int run_compress(zpaqgpu_ctx *ctx, CompressJob &job) {
         const size_t o_esegs = align_up(o_blocks + sizeof(EncBlock) * size_t(n_blocks), 16);
         const size_t o_pack = align_up(o_esegs + sizeof(EncSeg) * size_t(n_segs), 16);
         const size_t o_sha = align_up(o_pack + sizeof(PackSeg) * size_t(n_segs), 16);
-        const size_t o_pre = align_up(o_sha + sizeof(ShaJob) * size_t(n_segs), 16);
+        const size_t o_order = align_up(o_sha + sizeof(ShaJob) * size_t(n_segs), 16);
+        const size_t o_pre = align_up(o_order + sizeof(u32) * size_t(n_blocks), 16);
         const size_t desc_bytes = align_up(o_pre + pre.size() + 16, 16);
         int rc;
         if ((rc = ensure(ctx, ctx->desc, desc_bytes))) return rc;
@@ -266,6 +267,17 @@ int run_compress(zpaqgpu_ctx *ctx, CompressJob &job) {
         std::memcpy(blob.data() + o_esegs, esegs.data(), sizeof(EncSeg) * size_t(n_segs));
         std::memcpy(blob.data() + o_pack, pack.data(), sizeof(PackSeg) * size_t(n_segs));
         std::memcpy(blob.data() + o_sha, sha.data(), sizeof(ShaJob) * size_t(n_segs));
+        {   // dispatch order: largest blocks first (identity when all blocks have one size)
+            std::vector<u32> order(static_cast<size_t>(n_blocks));
+            std::vector<u64> weight(static_cast<size_t>(n_blocks), 0);
+            for (int b = 0; b < n_blocks; ++b) {
+                order[size_t(b)] = u32(b);
+                const EncBlock &blk = job.blocks[size_t(b)];
+                for (u32 k = 0; k < blk.n_seg; ++k) weight[size_t(b)] += job.segs[blk.first_seg + k].in_len;
+            }
+            std::stable_sort(order.begin(), order.end(), [&](u32 x, u32 y) { return weight[x] > weight[y]; });
+            std::memcpy(blob.data() + o_order, order.data(), sizeof(u32) * size_t(n_blocks));
+        }
         if (!pre.empty()) std::memcpy(blob.data() + o_pre, pre.data(), pre.size());
         CK(cudaMemcpyAsync(ctx->desc.p, blob.data(), desc_bytes, cudaMemcpyHostToDevice, st));
         CK(cudaStreamSynchronize(st));  // blob is a stack-lifetime host buffer
@@ -274,6 +286,7 @@ int run_compress(zpaqgpu_ctx *ctx, CompressJob &job) {
         const EncSeg *d_esegs = reinterpret_cast<const EncSeg *>(dbase + o_esegs);
         const PackSeg *d_pack = reinterpret_cast<const PackSeg *>(dbase + o_pack);
         const ShaJob *d_sha = reinterpret_cast<const ShaJob *>(dbase + o_sha);
+        const u32 *d_order = reinterpret_cast<const u32 *>(dbase + o_order);
         const u8 *d_pre = dbase + o_pre;
 
         // SHA-1 of the plaintext runs beside the codec on the side stream (compressor.v:284)
@@ -317,7 +330,7 @@ int run_compress(zpaqgpu_ctx *ctx, CompressJob &job) {
                     ea.workspace = static_cast<u8 *>(ctx->workspace.p);
                     ea.in = job.d_in, ea.arena = static_cast<u8 *>(ctx->arena.p);
                     ea.blocks = d_blocks, ea.segs = d_esegs, ea.pay_len = static_cast<u64 *>(ctx->pay_len.p);
-                    ea.first_block = first, ea.n_blocks = n;
+                    ea.order = d_order, ea.first_block = first, ea.n_blocks = n;
                     ea.flags = std::getenv("ZPAQGPU_ENC_FLAGS") ? std::atoi(std::getenv("ZPAQGPU_ENC_FLAGS")) : 1;
                     if (chain) {
                         if (!launch_encode_pipe3(m, ea, wpc, st)) {
@@ -504,11 +517,27 @@ int run_decompress(zpaqgpu_ctx *ctx, DecompressJob &job, bool caller_owns_plain)
         }
         u32 seg_cap = u32(std::max(64, n * 2 + 64));
         for (int seg_try = 0; seg_try < 2; ++seg_try) {
-            if ((rc = ensure(ctx, ctx->desc, sizeof(DecBlock) * size_t(n) + 16))) return rc;
+            const size_t o_dorder = align_up(sizeof(DecBlock) * size_t(n), 16);
+            if ((rc = ensure(ctx, ctx->desc, o_dorder + sizeof(u32) * size_t(n) + 16))) return rc;
             if ((rc = ensure(ctx, ctx->results, sizeof(DecBlockOut) * size_t(n) + 16))) return rc;
             if ((rc = ensure(ctx, ctx->seg_recs, sizeof(DecSegRec) * size_t(seg_cap) + 16))) return rc;
             if ((rc = ensure(ctx, ctx->misc, 64))) return rc;
             CK(cudaMemcpyAsync(ctx->desc.p, blocks.data(), sizeof(DecBlock) * size_t(n), cudaMemcpyHostToDevice, st));
+            {   // dispatch order: inside every run of blocks with one model, largest plaintext first
+                std::vector<u32> order(static_cast<size_t>(n));
+                for (int k = 0; k < n; ++k) order[size_t(k)] = u32(k);
+                int a = 0;
+                while (a < n) {
+                    int b = a;
+                    while (b < n && job.cand[size_t(b)].group == job.cand[size_t(a)].group) ++b;
+                    std::stable_sort(order.begin() + a, order.begin() + b,
+                                     [&](u32 x, u32 y) { return blocks[x].out_cap > blocks[y].out_cap; });
+                    a = b;
+                }
+                CK(cudaMemcpyAsync(static_cast<u8 *>(ctx->desc.p) + o_dorder, order.data(), sizeof(u32) * size_t(n),
+                                   cudaMemcpyHostToDevice, st));
+                CK(cudaStreamSynchronize(st));  // order is a stack-lifetime host buffer
+            }
             CK(cudaMemsetAsync(ctx->misc.p, 0, 64, st));
             CK(cudaMemsetAsync(ctx->results.p, 0, sizeof(DecBlockOut) * size_t(n), st));
             CK(cudaStreamSynchronize(st));
@@ -555,6 +584,7 @@ int run_decompress(zpaqgpu_ctx *ctx, DecompressJob &job, bool caller_owns_plain)
                             da.seg_recs = static_cast<DecSegRec *>(ctx->seg_recs.p);
                             da.seg_count = static_cast<u32 *>(ctx->misc.p);
                             da.seg_cap = seg_cap, da.first_block = first, da.n_blocks = cnt;
+                            da.order = reinterpret_cast<const u32 *>(static_cast<const u8 *>(ctx->desc.p) + o_dorder);
                             da.flags = ctx->spec_probe ? 1 : 0;
                             CK(cudaEventRecord(ctx->ev[0], st));
                             if (store) {

@@ -15,7 +15,9 @@ struct EncodeArgs {
     const EncBlock *blocks;  // all blocks of the call
     const EncSeg *segs;
     u64 *pay_len;            // per segment: coded payload bytes (counted even past pay_cap)
-    int first_block;         // wave offset into blocks[]
+    const u32 *order;        // dispatch order: slot k of the wave codes block order[first_block + k]
+                             // (largest blocks first, so that CTAs hold blocks of similar length)
+    int first_block;         // wave offset into order[]
     int n_blocks;            // blocks in this wave
     int flags;               // 1: the history warp pulls the next nibble's slot line into L1 one step early
 };
@@ -32,6 +34,7 @@ struct DecodeArgs {
     DecSegRec *seg_recs;
     u32 *seg_count;
     u32 seg_cap;
+    const u32 *order;        // dispatch order, as in EncodeArgs
     int first_block;
     int n_blocks;
     int flags;               // tree decoder: 1 = request the next nibble's candidate slots two bits early

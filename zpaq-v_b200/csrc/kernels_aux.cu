@@ -256,7 +256,7 @@ void launch_find_blocks(const u8 *arc, u64 len, u64 *starts, u32 cap, u32 *count
 __global__ void k_decode_store(DecodeArgs A) {
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (warp >= A.n_blocks) return;
-    const int bi = A.first_block + warp;
+    const int bi = int(A.order[A.first_block + warp]);
     const DecBlock blk = A.blocks[bi];
     const u8 *arc = A.arc;
     u64 pos = blk.arc_pos;

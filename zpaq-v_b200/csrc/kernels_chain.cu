@@ -699,7 +699,7 @@ __global__ void __launch_bounds__(256, 1) k_decode_chain(DecodeArgs A) {
     const int wic = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int slot = blockIdx.x * (blockDim.x >> 5) + wic;
     if (slot >= A.n_blocks) return;
-    const int bi = A.first_block + slot;
+    const int bi = int(A.order[A.first_block + slot]);
     typename std::conditional<TREE, Tree<NI, MIX2>, Chain<NI, MIX2>>::type C;
     u8 *ws = A.workspace + u64(slot) * A.model.ws_bytes;
     C.setup(smem + kSharedTables + size_t(wic) * warp_smem_bytes(NI, MIX2), A.model, ws,

@@ -173,7 +173,8 @@ __global__ void __launch_bounds__(672, 1) k_encode_pipe3(EncodeArgs A, int block
     }
     int2 *tab = V.tab + (owner ? lane : 0) * 256;
 
-    const EncBlock blk = A.blocks[A.first_block + slot];
+    const u32 bi = A.order[A.first_block + slot];
+    const EncBlock blk = A.blocks[bi];
     for (u32 s = 0; s < blk.n_seg; ++s) {
         const EncSeg seg = A.segs[blk.first_seg + s];
         const u8 *src = A.in + seg.in_off;

@@ -449,7 +449,7 @@ __global__ void __launch_bounds__(128) k_encode_generic(EncodeArgs A) {
     g.M = &A.model, g.T = A.tables;
     g.ws = A.workspace + u64(warp) * A.model.ws_bytes;
     g.block_init();
-    const EncBlock blk = A.blocks[A.first_block + warp];
+    const EncBlock blk = A.blocks[A.order[A.first_block + warp]];
     for (u32 s = 0; s < blk.n_seg; ++s) {
         const EncSeg seg = A.segs[blk.first_seg + s];
         Sink out{A.arena + seg.pay_off, seg.pay_cap, 0};
@@ -481,7 +481,7 @@ __global__ void __launch_bounds__(128) k_encode_generic(EncodeArgs A) {
 __global__ void __launch_bounds__(128) k_decode_generic(DecodeArgs A) {
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (warp >= A.n_blocks || (threadIdx.x & 31) != 0) return;
-    const int bi = A.first_block + warp;
+    const int bi = int(A.order[A.first_block + warp]);
     Gen g;
     g.M = &A.model, g.T = A.tables;
     g.ws = A.workspace + u64(warp) * A.model.ws_bytes;

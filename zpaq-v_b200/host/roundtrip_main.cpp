@@ -34,5 +34,12 @@ int main(int argc, char **argv) {
     const bool same = back.bytes() == input;
     for (uint8_t b : out.bytes()) std::printf("%02x", b);
     std::printf("\n%d %d %d\n", segs, ok, same ? 1 : 0);
+    // JidacArchive.create_archive (jidac.v:181) of two files made of the input: printed as a third line
+    zpaq::FileWriter jw;
+    zpaq::JidacArchive ja(20260101120000LL);
+    ja.set_output(&jw);
+    ja.create_archive({{"a", input}, {"b", std::vector<uint8_t>(input.rbegin(), input.rend())}}, 0);
+    for (uint8_t b : jw.bytes()) std::printf("%02x", b);
+    std::printf("\n");
     return same && segs == 1 && ok == 1 ? 0 : 1;
 }

@@ -6,6 +6,7 @@
 #include <cstdint>
 #include <stdexcept>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "zpaqgpu.h"
@@ -158,6 +159,50 @@ class Decompresser {
     int block_ = -1, cur_ = -1;
     size_t cursor_ = 0;
     uint64_t served_ = 0;
+};
+
+// jidac.v:120-296 -- JidacArchive: create_archive writes c, d.., h.., i blocks to the Writer.
+// `files` is an ordered list (a V map iterates in insertion order, which fixes the archive order).
+class JidacArchive {
+  public:
+    explicit JidacArchive(int64_t date) : date_(date) {}          // date: get_jidac_date(), jidac.v:31-35
+    void set_output(Writer *w) { out_ = w; }
+    // the reference ignores `method` and always stores the d blocks (jidac.v:94-118)
+    void create_archive(const std::vector<std::pair<std::string, std::vector<uint8_t>>> &files, int /*method*/) {
+        run(files, 0, -1, false, 0);
+    }
+    // `jidac add`: rolling-hash fragments, SHA-1 dedup, stored fragments packed into coded d blocks
+    void add(const std::vector<std::pair<std::string, std::vector<uint8_t>>> &files, int level, int fragment,
+             uint64_t block_bytes) {
+        run(files, level, fragment, true, block_bytes);
+    }
+  private:
+    void run(const std::vector<std::pair<std::string, std::vector<uint8_t>>> &files, int level, int fragment,
+             bool dedup, uint64_t block_bytes) {
+        if (!out_) return;                                        // jidac.v:182-184
+        std::vector<uint8_t> data;
+        std::vector<uint64_t> off{0};
+        std::vector<const char *> names;
+        for (const auto &f : files) {
+            data.insert(data.end(), f.second.begin(), f.second.end());
+            off.push_back(data.size());
+            names.push_back(f.first.c_str());
+        }
+        zpaqgpu_jidac_opts o{};
+        o.date = date_, o.level = level, o.fragment = fragment, o.dedup = dedup ? 1 : 0, o.block_bytes = block_bytes;
+        uint64_t got = 0, need = 0;
+        std::vector<uint8_t> arc(data.size() + data.size() / 4 + 4096 * (files.size() + 4));
+        int rc = zpaqgpu_jidac_add(Gpu::ctx(), &o, names.data(), data.data(), off.data(), int(files.size()), arc.data(),
+                                   arc.size(), &got, &need);
+        if (rc == ZPAQGPU_E_NOSPACE) {
+            arc.resize(need);
+            rc = zpaqgpu_jidac_add(Gpu::ctx(), &o, names.data(), data.data(), off.data(), int(files.size()), arc.data(),
+                                   arc.size(), &got, &need);
+        }
+        if (rc == ZPAQGPU_OK) out_->write(arc.data(), size_t(got));
+    }
+    int64_t date_;
+    Writer *out_ = nullptr;
 };
 
 }  // namespace zpaq
