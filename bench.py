@@ -214,6 +214,7 @@ def main():
     if world > 1:
         import torch.distributed as dist_
         dist = dist_
+        os.environ["NCCL_DEBUG"] = "WARN"  # rank 0 prints ONE JSON line on stdout: no NCCL version banner
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     level, nb, bb = args.level, args.blocks, args.block_kib * 1024
