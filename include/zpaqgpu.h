@@ -205,6 +205,25 @@ int zpaqgpu_jidac_add(zpaqgpu_ctx *ctx, const zpaqgpu_jidac_opts *opts, const ch
                       const uint8_t *in, const uint64_t *in_off, int n_files, uint8_t *out,
                       uint64_t out_cap, uint64_t *out_len, uint64_t *out_need);
 
+/* Restores the files of a journaling archive (north_star: `jidac extract`; the reference has only the
+ * writer, jidac.v:181-296, so this follows the layout that writer defines).  Every block is decoded on
+ * the device, the h tables (bsize[4] (sha1[20] usize[4])..., jidac.v:229-259) and the i blocks
+ * (date[8] name 0 na[4] attr[na] ni[4] ptr[ni][4], jidac.v:262-295; date 0 removes an earlier entry)
+ * are followed, the fragments of each file are gathered on the device and copied out once.
+ * `out` receives the files back to back in index order, `names` their NUL-terminated names.
+ * sha1_ok: 1 when every fragment of the file hashes to the SHA-1 its h table records, else 0.
+ * ZPAQGPU_E_NOSPACE sets *out_need / *n_files / *names_need; ZPAQGPU_E_FORMAT: tables inconsistent. */
+typedef struct {
+    uint64_t name_off;    /* inside `names`                                   */
+    uint64_t out_off, out_len;
+    int64_t date;         /* YYYYMMDDHHMMSS as stored                         */
+    int32_t n_fragments;
+    int32_t sha1_ok;
+} zpaqgpu_jidac_file;
+int zpaqgpu_jidac_extract(zpaqgpu_ctx *ctx, const uint8_t *arc, uint64_t len, uint8_t *out, uint64_t out_cap,
+                          uint64_t *out_need, zpaqgpu_jidac_file *files, int files_cap, int *n_files,
+                          char *names, uint64_t names_cap, uint64_t *names_need);
+
 typedef struct {
     float h2d_ms, fragment_ms, sha1_ms, dedup_ms, gather_ms; /* front-end stages            */
     float codec_ms;        /* d-block codec kernel                                           */

@@ -78,7 +78,33 @@ def test_add_matches_oracle_and_extracts(gpu_ctx, level, fragment, dedup, block_
         assert st["stored_bytes"] < st["input_bytes"]
     back = z.jidac.extract(got, gpu_ctx)
     assert back == files
+    assert list(back) == names                      # index order
+    assert z.jidac.extract_on_host(got, gpu_ctx) == files
     gpu_ctx.set_workspace_limit(0)
+
+
+def test_extract_details(gpu_ctx):
+    """Per-file records of zpaqgpu_jidac_extract; a damaged fragment is reported, a damaged table refused."""
+    import zpaq_v_b200 as z
+    files = {"a.txt": datagen.text(30000, 3), "empty": b"", "b.bin": datagen.random_bytes(9000, 4),
+             "a-again": datagen.text(30000, 3)}
+    arc = gpu_ctx.jidac_add(list(files), list(files.values()), DATE, level=0, fragment=0, dedup=True, block_bytes=0)
+    recs = gpu_ctx.jidac_extract(arc)
+    assert [r["name"] for r in recs] == list(files)
+    assert all(r["data"] == files[r["name"]] and r["sha1_ok"] == 1 and r["date"] == DATE for r in recs)
+    assert recs[1]["n_fragments"] == 0 and recs[0]["n_fragments"] == recs[3]["n_fragments"] > 1
+    assert gpu_ctx.jidac_extract(b"") == []
+    assert gpu_ctx.jidac_extract(gpu_ctx.jidac_add([], [], DATE)) == []
+    # the reference's own create_archive bytes (from the oracle) extract as well
+    ref = ob.jidac_add(list(files), list(files.values()), DATE)
+    assert {r["name"]: r["data"] for r in gpu_ctx.jidac_extract(ref)} == files
+    # flip one stored byte of the first d block (store mode: plaintext sits in the archive): the block
+    # checksum no longer matches and the call refuses the archive
+    at = arc.index(files["a.txt"][:64])
+    bad = bytearray(arc)
+    bad[at + 10] ^= 1
+    with pytest.raises(z.ZpaqGpuError):
+        gpu_ctx.jidac_extract(bytes(bad))
 
 
 def test_mirror_class(gpu_ctx):

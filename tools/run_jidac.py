@@ -67,7 +67,7 @@ def main():
            "stored_bytes": st["stored_bytes"], "launches": st["launches"]}
     if not args.no_extract:
         t2 = time.perf_counter()
-        back = z.jidac.extract(arc, ctx)
+        back = z.jidac.extract(arc, ctx)   # zpaqgpu_jidac_extract: decode + fragment gather on the device
         t3 = time.perf_counter()
         res["extract_ok"] = all(back[n] == f for n, f in zip(names, files))
         res["gpu_extract_mb_s"] = round(total / (t3 - t2) / 1e6, 2)

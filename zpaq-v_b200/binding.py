@@ -21,7 +21,7 @@ EXPORTS = [
     "zpaqgpu_find_blocks", "zpaqgpu_decompress_archive", "zpaqgpu_decompress_blocks_dev",
     "zpaqgpu_block_begin", "zpaqgpu_block_begin_header", "zpaqgpu_segment_begin", "zpaqgpu_segment_write",
     "zpaqgpu_segment_end", "zpaqgpu_block_end", "zpaqgpu_last_stats", "zpaqgpu_describe_model",
-    "zpaqgpu_jidac_fragment", "zpaqgpu_jidac_add", "zpaqgpu_jidac_last_stats",
+    "zpaqgpu_jidac_fragment", "zpaqgpu_jidac_add", "zpaqgpu_jidac_extract", "zpaqgpu_jidac_last_stats",
 ]
 
 
@@ -57,6 +57,11 @@ class JidacOpts(C.Structure):
 class Fragment(C.Structure):
     _fields_ = [("off", C.c_uint64), ("len", C.c_uint64), ("file", C.c_uint32), ("id", C.c_uint32),
                 ("stored", C.c_uint32), ("sha1", C.c_uint8 * 20)]
+
+
+class JidacFile(C.Structure):
+    _fields_ = [("name_off", C.c_uint64), ("out_off", C.c_uint64), ("out_len", C.c_uint64), ("date", C.c_int64),
+                ("n_fragments", C.c_int32), ("sha1_ok", C.c_int32)]
 
 
 class JidacStats(C.Structure):
@@ -120,6 +125,8 @@ def lib():
     L.zpaqgpu_jidac_fragment.argtypes = [vp, vp, vp, C.c_int, C.c_int, C.c_int, vp, C.c_int, i32p, i32p]
     L.zpaqgpu_jidac_add.argtypes = [vp, C.POINTER(JidacOpts), vp, vp, vp, C.c_int, vp, C.c_uint64, u64p, u64p]
     L.zpaqgpu_jidac_last_stats.argtypes = [vp, C.POINTER(JidacStats)]
+    L.zpaqgpu_jidac_extract.argtypes = [vp, vp, C.c_uint64, vp, C.c_uint64, u64p, vp, C.c_int, i32p, vp, C.c_uint64,
+                                        u64p]
     _lib = L
     return L
 
@@ -327,6 +334,30 @@ class Context:
                 continue
             self._check(rc)
             return out.raw[:ln.value]
+        raise ZpaqGpuError(E_NOSPACE, "output sizing did not converge")
+
+    def jidac_extract(self, arc):
+        """Files of a journaling archive: list of dicts name/data/date/n_fragments/sha1_ok, index order."""
+        arc = bytes(arc)
+        out_cap, files_cap, names_cap = max(4 * len(arc), 1 << 16), 1024, 1 << 16
+        need, nf, nn = C.c_uint64(0), C.c_int(0), C.c_uint64(0)
+        for _ in range(3):
+            out = C.create_string_buffer(out_cap)
+            files = (JidacFile * files_cap)()
+            names = C.create_string_buffer(names_cap)
+            rc = lib().zpaqgpu_jidac_extract(self._h, arc, len(arc), out, out_cap, C.byref(need), files, files_cap,
+                                             C.byref(nf), names, names_cap, C.byref(nn))
+            if rc == E_NOSPACE:
+                out_cap, files_cap, names_cap = need.value + 16, nf.value + 16, nn.value + 16
+                continue
+            self._check(rc)
+            raw, nraw = out.raw, names.raw
+            res = []
+            for f in files[:nf.value]:
+                name = nraw[f.name_off:nraw.index(b"\0", f.name_off)].decode("latin1")
+                res.append(dict(name=name, data=raw[f.out_off:f.out_off + f.out_len], date=f.date,
+                                n_fragments=f.n_fragments, sha1_ok=f.sha1_ok))
+            return res
         raise ZpaqGpuError(E_NOSPACE, "output sizing did not converge")
 
     def jidac_stats(self):

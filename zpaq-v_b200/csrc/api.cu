@@ -723,6 +723,112 @@ u64 comment_hint(const uint8_t *arc, u64 len, u64 payload) {
     return v;
 }
 
+// Steps 1-4 of decoding a whole archive: the archive goes to the device, every block is found and
+// decoded into the plaintext arena (ctx->plain), and the segments are listed the way repeated
+// find_block / find_filename calls would meet them.  *status carries what the walk ended with.
+int decode_archive_dev(zpaqgpu_ctx *ctx, const uint8_t *arc, u64 len, std::vector<DecodedSeg> &segs,
+                       const u8 **d_plain, int *status_out, u64 *total_out) {
+    segs.clear();
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    int rc;
+    // 1. archive to the device, locator scan
+    if ((rc = ensure(ctx, ctx->in, len))) return rc;
+    CK(cudaEventRecord(ctx->ev[6], st));
+    CK(cudaMemcpyAsync(ctx->in.p, arc, len, cudaMemcpyHostToDevice, st));
+    CK(cudaEventRecord(ctx->ev[7], st));
+    u32 dcap = 1u << 16;
+    std::vector<u64> starts;
+    for (;;) {
+        if ((rc = ensure(ctx, ctx->results, 8 * size_t(dcap)))) return rc;
+        if ((rc = ensure(ctx, ctx->misc, 64))) return rc;
+        CK(cudaMemsetAsync(ctx->misc.p, 0, 64, st));
+        launch_find_blocks(static_cast<const u8 *>(ctx->in.p), len, static_cast<u64 *>(ctx->results.p), dcap,
+                           static_cast<u32 *>(ctx->misc.p), st);
+        CK(cudaGetLastError());
+        u32 count = 0;
+        CK(cudaMemcpyAsync(&count, ctx->misc.p, 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        if (count > dcap) { dcap = count + 1024; continue; }
+        starts.resize(count);
+        if (count) CK(cudaMemcpy(starts.data(), ctx->results.p, 8 * size_t(count), cudaMemcpyDeviceToHost));
+        break;
+    }
+    const float h2d_ms = elapsed(ctx->ev[6], ctx->ev[7]);
+    std::sort(starts.begin(), starts.end());
+    // 2. headers (decompressor.v:257-342).  Every candidate is decoded optimistically; candidates
+    //    that turn out to lie inside an earlier block are dropped in step 4.
+    DecompressJob job;
+    job.d_arc = static_cast<const u8 *>(ctx->in.p), job.arc_len = len;
+    std::map<std::vector<uint8_t>, int> group_of;
+    for (u64 s : starts) {
+        DecCandidate c;
+        c.start = s;
+        Model m;
+        u64 used = 0;
+        const int hrc = model_from_archive(arc + s, len - s, m, &used);
+        c.payload = s + used;
+        if (hrc == ZPAQGPU_OK) {
+            auto it = group_of.find(m.header);
+            if (it == group_of.end()) {
+                it = group_of.emplace(m.header, int(job.models.size())).first;
+                job.models.push_back(m);
+            }
+            c.group = it->second;
+            const u64 hint = comment_hint(arc, len, c.payload);
+            c.hint = hint ? hint : 4 * (len - c.payload > (1u << 20) ? (1u << 20) : len - c.payload) + 65536;
+        } else {
+            c.group = hrc == ZPAQGPU_E_UNSUPPORTED ? -2 : -1;
+            c.hint = 0;
+        }
+        job.cand.push_back(c);
+    }
+    // 3. decode
+    if (!job.cand.empty() && !job.models.empty()) {
+        // rejected headers get a dummy group so indices stay aligned; they are never launched
+        if ((rc = run_decompress(ctx, job, false))) return rc;
+    }
+    ctx->stats.h2d_ms = h2d_ms;
+    ctx->stats.pack_ms = 0;
+    // 4. walk the candidates the way repeated find_block calls would (decompressor.v:219-346)
+    u64 pos = 0, total = 0;
+    int seg_total = 0, block_index = 0;
+    int status = ZPAQGPU_OK;
+    size_t rec_at = 0;
+    for (size_t i = 0; i < job.cand.size(); ++i) {
+        const DecCandidate &c = job.cand[i];
+        // a later find_block call restarts its rolling hashes at `pos`, so it only sees locators
+        // that lie completely behind the previous block; anything earlier is inside that block
+        if (pos > 0 && c.start < pos + 16) continue;
+        if (c.group < 0) {
+            // find_block returns false here and `for find_block {}` ends (cmd/main.v:349)
+            status = c.group == -2 ? ZPAQGPU_E_UNSUPPORTED : ZPAQGPU_OK;
+            break;
+        }
+        while (rec_at < job.recs.size() && job.recs[rec_at].block < u32(i)) ++rec_at;
+        size_t r = rec_at;
+        for (; r < job.recs.size() && job.recs[r].block == u32(i); ++r) {
+            const DecSegRec &rec = job.recs[r];
+            DecodedSeg ds;
+            ds.seg.block_start = c.start, ds.seg.block_end = c.res.end_pos;
+            ds.seg.name_off = rec.name_off, ds.seg.comment_off = rec.comment_off;
+            ds.seg.out_off = total, ds.seg.out_len = rec.out_len;
+            ds.seg.block_index = block_index, ds.seg.sha1_ok = job.sha_ok[r];
+            ds.src = rec.out_off;
+            segs.push_back(ds);
+            total += rec.out_len;
+            ++seg_total;
+        }
+        if (c.res.status != ZPAQGPU_OK && status == ZPAQGPU_OK) status = c.res.status;
+        pos = c.res.end_pos;
+        ++block_index;
+        if (c.res.status != ZPAQGPU_OK) break;
+    }
+    (void)seg_total;
+    *d_plain = job.d_plain, *status_out = status, *total_out = total;
+    return ZPAQGPU_OK;
+}
+
 }  // namespace
 
 // ============================================================================================
@@ -982,104 +1088,16 @@ int zpaqgpu_decompress_archive(zpaqgpu_ctx *ctx, const uint8_t *arc, uint64_t le
     if (out_need) *out_need = 0;
     if (n_segs) *n_segs = 0;
     if (len == 0) return ZPAQGPU_OK;
-    CK(cudaSetDevice(ctx->device));
-    cudaStream_t st = ctx->stream;
-    int rc;
-    // 1. archive to the device, locator scan
-    if ((rc = ensure(ctx, ctx->in, len))) return rc;
-    CK(cudaEventRecord(ctx->ev[6], st));
-    CK(cudaMemcpyAsync(ctx->in.p, arc, len, cudaMemcpyHostToDevice, st));
-    CK(cudaEventRecord(ctx->ev[7], st));
-    u32 dcap = 1u << 16;
-    std::vector<u64> starts;
-    for (;;) {
-        if ((rc = ensure(ctx, ctx->results, 8 * size_t(dcap)))) return rc;
-        if ((rc = ensure(ctx, ctx->misc, 64))) return rc;
-        CK(cudaMemsetAsync(ctx->misc.p, 0, 64, st));
-        launch_find_blocks(static_cast<const u8 *>(ctx->in.p), len, static_cast<u64 *>(ctx->results.p), dcap,
-                           static_cast<u32 *>(ctx->misc.p), st);
-        CK(cudaGetLastError());
-        u32 count = 0;
-        CK(cudaMemcpyAsync(&count, ctx->misc.p, 4, cudaMemcpyDeviceToHost, st));
-        CK(cudaStreamSynchronize(st));
-        if (count > dcap) { dcap = count + 1024; continue; }
-        starts.resize(count);
-        if (count) CK(cudaMemcpy(starts.data(), ctx->results.p, 8 * size_t(count), cudaMemcpyDeviceToHost));
-        break;
-    }
-    const float h2d_ms = elapsed(ctx->ev[6], ctx->ev[7]);
-    std::sort(starts.begin(), starts.end());
-    // 2. headers (decompressor.v:257-342).  Every candidate is decoded optimistically; candidates
-    //    that turn out to lie inside an earlier block are dropped in step 4.
-    DecompressJob job;
-    job.d_arc = static_cast<const u8 *>(ctx->in.p), job.arc_len = len;
-    std::map<std::vector<uint8_t>, int> group_of;
-    for (u64 s : starts) {
-        DecCandidate c;
-        c.start = s;
-        Model m;
-        u64 used = 0;
-        const int hrc = model_from_archive(arc + s, len - s, m, &used);
-        c.payload = s + used;
-        if (hrc == ZPAQGPU_OK) {
-            auto it = group_of.find(m.header);
-            if (it == group_of.end()) {
-                it = group_of.emplace(m.header, int(job.models.size())).first;
-                job.models.push_back(m);
-            }
-            c.group = it->second;
-            const u64 hint = comment_hint(arc, len, c.payload);
-            c.hint = hint ? hint : 4 * (len - c.payload > (1u << 20) ? (1u << 20) : len - c.payload) + 65536;
-        } else {
-            c.group = hrc == ZPAQGPU_E_UNSUPPORTED ? -2 : -1;
-            c.hint = 0;
-        }
-        job.cand.push_back(c);
-    }
-    // 3. decode
-    if (!job.cand.empty() && !job.models.empty()) {
-        // rejected headers get a dummy group so indices stay aligned; they are never launched
-        if ((rc = run_decompress(ctx, job, false))) return rc;
-    }
-    ctx->stats.h2d_ms = h2d_ms;
-    ctx->stats.pack_ms = 0;
-    // 4. walk the candidates the way repeated find_block calls would (decompressor.v:219-346)
-    u64 pos = 0, total = 0;
-    int seg_total = 0, block_index = 0;
+    std::vector<DecodedSeg> list;
+    const u8 *d_plain = nullptr;
     int status = ZPAQGPU_OK;
-    struct Piece { u64 src, len; };
-    std::vector<Piece> pieces;
-    size_t rec_at = 0;
-    for (size_t i = 0; i < job.cand.size(); ++i) {
-        const DecCandidate &c = job.cand[i];
-        // a later find_block call restarts its rolling hashes at `pos`, so it only sees locators
-        // that lie completely behind the previous block; anything earlier is inside that block
-        if (pos > 0 && c.start < pos + 16) continue;
-        if (c.group < 0) {
-            // find_block returns false here and `for find_block {}` ends (cmd/main.v:349)
-            status = c.group == -2 ? ZPAQGPU_E_UNSUPPORTED : ZPAQGPU_OK;
-            break;
-        }
-        while (rec_at < job.recs.size() && job.recs[rec_at].block < u32(i)) ++rec_at;
-        size_t r = rec_at;
-        for (; r < job.recs.size() && job.recs[r].block == u32(i); ++r) {
-            const DecSegRec &rec = job.recs[r];
-            if (segs && seg_total < segs_cap) {
-                zpaqgpu_segment &o = segs[seg_total];
-                o.block_start = c.start, o.block_end = c.res.end_pos;
-                o.name_off = rec.name_off, o.comment_off = rec.comment_off;
-                o.out_off = total, o.out_len = rec.out_len;
-                o.block_index = block_index, o.sha1_ok = job.sha_ok[r];
-            }
-            pieces.push_back(Piece{rec.out_off, rec.out_len});
-            total += rec.out_len;
-            ++seg_total;
-        }
-        if (c.res.status != ZPAQGPU_OK && status == ZPAQGPU_OK) status = c.res.status;
-        pos = c.res.end_pos;
-        ++block_index;
-        if (c.res.status != ZPAQGPU_OK) break;
-    }
+    u64 total = 0;
+    int rc = decode_archive_dev(ctx, arc, len, list, &d_plain, &status, &total);
+    if (rc) return rc;
+    cudaStream_t st = ctx->stream;
+    const int seg_total = int(list.size());
+    if (segs)
+        for (int k = 0; k < seg_total && k < segs_cap; ++k) segs[k] = list[size_t(k)].seg;
     if (out_need) *out_need = total;
     if (n_segs) *n_segs = seg_total;
     if (total > out_cap || (segs && seg_total > segs_cap)) return ZPAQGPU_E_NOSPACE;
@@ -1087,11 +1105,11 @@ int zpaqgpu_decompress_archive(zpaqgpu_ctx *ctx, const uint8_t *arc, uint64_t le
     // 5. plaintext back to the host: contiguous runs of the arena are merged into single copies
     CK(cudaEventRecord(ctx->ev[6], st));
     u64 dst = 0;
-    for (size_t k = 0; k < pieces.size();) {
-        u64 src = pieces[k].src, run = pieces[k].len;
+    for (size_t k = 0; k < list.size();) {
+        u64 src = list[k].src, run = list[k].seg.out_len;
         size_t j = k + 1;
-        while (j < pieces.size() && pieces[j].src == src + run) run += pieces[j].len, ++j;
-        if (run) CK(cudaMemcpyAsync(out + dst, job.d_plain + src, run, cudaMemcpyDeviceToHost, st));
+        while (j < list.size() && list[j].src == src + run) run += list[j].seg.out_len, ++j;
+        if (run) CK(cudaMemcpyAsync(out + dst, d_plain + src, run, cudaMemcpyDeviceToHost, st));
         dst += run;
         k = j;
     }

@@ -94,4 +94,14 @@ float elapsed(cudaEvent_t a, cudaEvent_t b);
 // blocks of segments, plaintext already on the device -> archive bytes on the device
 int run_compress(zpaqgpu_ctx *ctx, CompressJob &job);
 
+// A decoded segment: the public record plus where its plaintext sits in the device arena.
+struct DecodedSeg {
+    zpaqgpu_segment seg;
+    u64 src;
+};
+// Whole archive (host bytes) -> plaintext of every segment in the device arena, segments in the order
+// find_block / find_filename meet them (decompressor.v:219-635).
+int decode_archive_dev(zpaqgpu_ctx *ctx, const uint8_t *arc, u64 len, std::vector<DecodedSeg> &segs,
+                       const u8 **d_plain, int *status, u64 *total);
+
 }  // namespace zg

@@ -260,6 +260,27 @@ __global__ void k_gather_fragments(const u8 *in, const ShaJob *jobs, const u32 *
     }
 }
 
+struct CopyJob {
+    u64 src, dst, len;
+};
+// one CTA per range: fragments of the d blocks -> their place in the restored files
+__global__ void k_copy_ranges(const u8 *src_base, u8 *dst_base, const CopyJob *jobs) {
+    const CopyJob j = jobs[blockIdx.x];
+    const u8 *s = src_base + j.src;
+    u8 *d = dst_base + j.dst;
+    if (((reinterpret_cast<uintptr_t>(s) ^ reinterpret_cast<uintptr_t>(d)) & 15) == 0) {
+        const u64 head = min(j.len, u64((16 - (reinterpret_cast<uintptr_t>(s) & 15)) & 15));
+        for (u64 k = threadIdx.x; k < head; k += blockDim.x) d[k] = s[k];
+        const u64 vec = (j.len - head) / 16;
+        const uint4 *sv = reinterpret_cast<const uint4 *>(s + head);
+        uint4 *dv = reinterpret_cast<uint4 *>(d + head);
+        for (u64 k = threadIdx.x; k < vec; k += blockDim.x) dv[k] = sv[k];
+        for (u64 k = head + vec * 16 + threadIdx.x; k < j.len; k += blockDim.x) d[k] = s[k];
+    } else {
+        for (u64 k = threadIdx.x; k < j.len; k += blockDim.x) d[k] = s[k];
+    }
+}
+
 // ---- host side ---------------------------------------------------------------------------
 
 struct Front {
@@ -476,6 +497,209 @@ int zpaqgpu_jidac_fragment(zpaqgpu_ctx *ctx, const uint8_t *in, const uint64_t *
         f.file = R.file_of[size_t(i)], f.id = R.id[size_t(i)], f.stored = R.stored[size_t(i)];
         std::memcpy(f.sha1, R.digests.data() + 20 * size_t(i), 20);
     }
+    return ZPAQGPU_OK;
+}
+
+int zpaqgpu_jidac_extract(zpaqgpu_ctx *ctx, const uint8_t *arc, uint64_t len, uint8_t *out, uint64_t out_cap,
+                          uint64_t *out_need, zpaqgpu_jidac_file *files, int files_cap, int *n_files, char *names,
+                          uint64_t names_cap, uint64_t *names_need) {
+    if (!ctx || (len && !arc)) return ZPAQGPU_E_ARG;
+    if (out_need) *out_need = 0;
+    if (n_files) *n_files = 0;
+    if (names_need) *names_need = 0;
+    if (len == 0) return ZPAQGPU_OK;
+    std::vector<DecodedSeg> segs;
+    const u8 *d_plain = nullptr;
+    int status = ZPAQGPU_OK;
+    u64 total = 0;
+    int rc = decode_archive_dev(ctx, arc, len, segs, &d_plain, &status, &total);
+    if (rc) return rc;
+    if (status != ZPAQGPU_OK) return status;
+    cudaStream_t st = ctx->stream;
+    ctx->jd_stats = zpaqgpu_jidac_stats{};
+    ctx->jd_stats.codec_ms = ctx->stats.codec_ms, ctx->jd_stats.h2d_ms = ctx->stats.h2d_ms;
+    ctx->jd_stats.launches = ctx->stats.launches;
+
+    // journaling blocks by kind: name = jDC<date14><kind><num10> (jidac.v:47-49)
+    struct JSeg { char kind; u32 num; const DecodedSeg *s; };
+    std::vector<JSeg> js;
+    for (const DecodedSeg &d : segs) {
+        const u64 at = d.seg.name_off;
+        if (at + 28 >= len || std::memcmp(arc + at, "jDC", 3) != 0 || arc[at + 28] != 0) continue;
+        bool ok = true;
+        u64 num = 0;
+        for (int k = 3; k < 17 && ok; ++k) ok = arc[at + k] >= '0' && arc[at + k] <= '9';
+        for (int k = 18; k < 28 && ok; ++k) ok = arc[at + k] >= '0' && arc[at + k] <= '9', num = num * 10 + (arc[at + k] - '0');
+        const char kind = char(arc[at + 17]);
+        if (!ok || (kind != 'c' && kind != 'd' && kind != 'h' && kind != 'i')) continue;
+        if (d.seg.sha1_ok == 0) {
+            ctx->err = "SHA-1 of a journaling block does not match";
+            return ZPAQGPU_E_FORMAT;
+        }
+        js.push_back(JSeg{kind, u32(num), &d});
+    }
+    // the index blocks are small: bring their plaintext to the host
+    u64 idx_bytes = 0;
+    for (const JSeg &j : js)
+        if (j.kind == 'h' || j.kind == 'i') idx_bytes += j.s->seg.out_len;
+    std::vector<u8> idx(static_cast<size_t>(idx_bytes) + 1);
+    {
+        u64 at = 0;
+        for (const JSeg &j : js)
+            if (j.kind == 'h' || j.kind == 'i') {
+                if (j.s->seg.out_len)
+                    CK(cudaMemcpyAsync(idx.data() + at, d_plain + j.s->src, j.s->seg.out_len, cudaMemcpyDeviceToHost, st));
+                at += j.s->seg.out_len;
+            }
+        CK(cudaStreamSynchronize(st));
+    }
+    auto le = [](const u8 *p, int n) { u64 v = 0; for (int i = 0; i < n; ++i) v |= u64(p[i]) << (8 * i); return v; };
+    // d blocks by their first fragment id; fragments from the h tables
+    struct Frag { u64 src; u32 len; u8 sha1[20]; bool known = false; };
+    std::vector<Frag> frags(1);  // ids are 1-based
+    std::vector<std::pair<u32, const DecodedSeg *>> dsegs;
+    for (const JSeg &j : js)
+        if (j.kind == 'd') dsegs.emplace_back(j.num, j.s);
+    struct FileRec { std::string name; i64 date; std::vector<u32> ptr; bool live; };
+    std::vector<FileRec> recs;
+    {
+        u64 at = 0;
+        for (const JSeg &j : js) {
+            if (j.kind != 'h' && j.kind != 'i') continue;
+            const u8 *p = idx.data() + at;
+            const u64 n = j.s->seg.out_len;
+            at += n;
+            if (j.kind == 'h') {
+                const DecodedSeg *dblk = nullptr;
+                for (const auto &d : dsegs)
+                    if (d.first == j.num) dblk = d.second;
+                if (!dblk || n < 4 || (n - 4) % 24 != 0) {
+                    ctx->err = "fragment table without its data block";
+                    return ZPAQGPU_E_FORMAT;
+                }
+                u64 off = 0;
+                u32 id = j.num;
+                for (u64 q = 4; q + 24 <= n; q += 24, ++id) {
+                    if (frags.size() <= id) frags.resize(size_t(id) + 1);
+                    Frag &f = frags[id];
+                    std::memcpy(f.sha1, p + q, 20);
+                    f.len = u32(le(p + q + 20, 4));
+                    f.src = dblk->src + off, f.known = true;
+                    off += f.len;
+                }
+                if (off != dblk->seg.out_len) {
+                    ctx->err = "fragment sizes do not add up to the data block";
+                    return ZPAQGPU_E_FORMAT;
+                }
+            } else {
+                u64 q = 0;
+                while (q + 8 <= n) {
+                    FileRec r;
+                    r.date = i64(le(p + q, 8)), q += 8;
+                    u64 e = q;
+                    while (e < n && p[e]) ++e;
+                    if (e >= n) return ctx->err = "unterminated name in the index", ZPAQGPU_E_FORMAT;
+                    r.name.assign(reinterpret_cast<const char *>(p + q), size_t(e - q));
+                    q = e + 1;
+                    r.live = r.date != 0;
+                    if (r.live) {
+                        if (q + 4 > n) return ctx->err = "truncated index entry", ZPAQGPU_E_FORMAT;
+                        const u64 na = le(p + q, 4);
+                        q += 4 + na;
+                        if (q + 4 > n) return ctx->err = "truncated index entry", ZPAQGPU_E_FORMAT;
+                        const u64 ni = le(p + q, 4);
+                        q += 4;
+                        if (q + 4 * ni > n) return ctx->err = "truncated index entry", ZPAQGPU_E_FORMAT;
+                        for (u64 k = 0; k < ni; ++k) r.ptr.push_back(u32(le(p + q + 4 * k, 4)));
+                        q += 4 * ni;
+                    }
+                    // a later entry of the same name replaces the earlier one; date 0 removes it
+                    for (FileRec &old : recs)
+                        if (old.live && old.name == r.name) old.live = false;
+                    recs.push_back(std::move(r));
+                }
+            }
+        }
+    }
+    // output layout and copy list
+    std::vector<CopyJob> jobs;
+    std::vector<const FileRec *> live;
+    u64 out_total = 0, name_total = 0;
+    for (const FileRec &r : recs) {
+        if (!r.live) continue;
+        live.push_back(&r);
+        name_total += r.name.size() + 1;
+        for (u32 id : r.ptr) {
+            if (id == 0 || id >= frags.size() || !frags[id].known)
+                return ctx->err = "index refers to an unknown fragment", ZPAQGPU_E_FORMAT;
+            if (frags[id].len) jobs.push_back(CopyJob{frags[id].src, out_total, frags[id].len});
+            out_total += frags[id].len;
+        }
+    }
+    if (out_need) *out_need = out_total;
+    if (n_files) *n_files = int(live.size());
+    if (names_need) *names_need = name_total;
+    if (out_total > out_cap || int(live.size()) > files_cap || name_total > names_cap) return ZPAQGPU_E_NOSPACE;
+    if ((out_total && !out) || (!live.empty() && (!files || !names))) return ZPAQGPU_E_ARG;
+    // SHA-1 of every known fragment against its table entry
+    const size_t nfr = frags.size();
+    std::vector<ShaJob> sj;
+    std::vector<u32> sj_id;
+    for (size_t id = 1; id < nfr; ++id)
+        if (frags[id].known) sj.push_back(ShaJob{frags[id].src, frags[id].len}), sj_id.push_back(u32(id));
+    std::vector<u8> dig(20 * sj.size() + 1);
+    std::vector<char> frag_ok(nfr, 0);
+    Timer t_sha, t_gather, t_d2h;
+    if (!sj.empty()) {
+        if ((rc = ensure(ctx, ctx->jd_frag, sizeof(ShaJob) * sj.size() + 20 * sj.size() + 64))) return rc;
+        u8 *fb = static_cast<u8 *>(ctx->jd_frag.p);
+        const size_t o_dig = align_up(sizeof(ShaJob) * sj.size(), 16);
+        CK(cudaMemcpyAsync(fb, sj.data(), sizeof(ShaJob) * sj.size(), cudaMemcpyHostToDevice, st));
+        t_sha.start(st);
+        launch_sha1(d_plain, reinterpret_cast<const ShaJob *>(fb), int(sj.size()), fb + o_dig, st);
+        t_sha.stop(st);
+        CK(cudaMemcpyAsync(dig.data(), fb + o_dig, 20 * sj.size(), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        ctx->jd_stats.sha1_ms = t_sha.ms();
+        ctx->jd_stats.launches += 1;
+        for (size_t k = 0; k < sj.size(); ++k)
+            frag_ok[sj_id[k]] = std::memcmp(dig.data() + 20 * k, frags[sj_id[k]].sha1, 20) == 0;
+    }
+    // gather on the device, one copy out
+    if (out_total) {
+        if ((rc = ensure(ctx, ctx->jd_packed, out_total))) return rc;
+        if ((rc = ensure(ctx, ctx->jd_small, sizeof(CopyJob) * jobs.size() + 16))) return rc;
+        if (!jobs.empty()) {
+            CK(cudaMemcpyAsync(ctx->jd_small.p, jobs.data(), sizeof(CopyJob) * jobs.size(), cudaMemcpyHostToDevice, st));
+            t_gather.start(st);
+            k_copy_ranges<<<unsigned(jobs.size()), 256, 0, st>>>(d_plain, static_cast<u8 *>(ctx->jd_packed.p),
+                                                                static_cast<const CopyJob *>(ctx->jd_small.p));
+            t_gather.stop(st);
+            CK(cudaGetLastError());
+            ctx->jd_stats.launches += 1;
+        }
+        t_d2h.start(st);
+        CK(cudaMemcpyAsync(out, ctx->jd_packed.p, out_total, cudaMemcpyDeviceToHost, st));
+        t_d2h.stop(st);
+        CK(cudaStreamSynchronize(st));
+        if (!jobs.empty()) ctx->jd_stats.gather_ms = t_gather.ms();
+        ctx->jd_stats.d2h_ms = t_d2h.ms();
+    }
+    u64 at = 0, nat = 0;
+    for (size_t k = 0; k < live.size(); ++k) {
+        const FileRec &r = *live[k];
+        zpaqgpu_jidac_file &f = files[k];
+        f.name_off = nat, f.out_off = at, f.date = r.date, f.n_fragments = int(r.ptr.size());
+        std::memcpy(names + nat, r.name.c_str(), r.name.size() + 1);
+        nat += r.name.size() + 1;
+        u64 flen = 0;
+        int ok = 1;
+        for (u32 id : r.ptr) flen += frags[id].len, ok &= frag_ok[id] ? 1 : 0;
+        f.out_len = flen, f.sha1_ok = ok;
+        at += flen;
+    }
+    ctx->jd_stats.n_files = int(live.size()), ctx->jd_stats.n_fragments = int(sj.size());
+    ctx->jd_stats.input_bytes = len, ctx->jd_stats.stored_bytes = total, ctx->jd_stats.archive_bytes = len;
     return ZPAQGPU_OK;
 }
 

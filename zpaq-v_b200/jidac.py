@@ -103,7 +103,20 @@ def parse_index(segments, plain):
 
 
 def extract(archive, ctx=None):
-    """Decode a journaling archive on the GPU and reassemble its files: dict name -> bytes."""
+    """Decode a journaling archive on the GPU and reassemble its files there (zpaqgpu_jidac_extract):
+    dict name -> bytes.  Raises when a fragment does not hash to the SHA-1 its table records."""
+    ctx = ctx or default_context()
+    out = {}
+    for f in ctx.jidac_extract(archive):
+        if not f["sha1_ok"]:
+            raise binding.ZpaqGpuError(binding.E_FORMAT, "SHA-1 mismatch in file " + f["name"])
+        out[f["name"]] = f["data"]
+    return out
+
+
+def extract_on_host(archive, ctx=None):
+    """The same result with the tables followed on the host (parse_index): kept as a cross-check of
+    the C ABI call in the tests."""
     ctx = ctx or default_context()
     plain, segs, status = ctx.decompress_archive(archive)
     if status != binding.OK:
