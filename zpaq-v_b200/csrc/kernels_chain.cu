@@ -75,11 +75,24 @@ struct Chain {
     int ctx_mode, n_hash, n_comp;
     u32 hist;          // CTX_M1: previous three bytes; CTX_HASHCHAIN: previous byte
     int lane;
+    // Probing role (speculative probe, as in the tree decoder): lane = (component pc = lane & 7,
+    // candidate pcand = lane >> 3).  Lanes 0..NI are candidate 0 of their own component.
+    int pc;
+    u32 pcand;
+    bool powner, spec;
+    uint4 q0, q1, q2;  // candidate slots of the NEXT nibble, requested two bits early
+    u8 *qb0;
+    u32 q_key, cur_vline;
+    bool q_ok;
 
     __device__ void setup(u8 *smem_warp, const ModelDev &M, u8 *ws, const int16_t *st, const u16 *sq,
                           const u8 *nx) {
         lane = threadIdx.x & 31;
         owner = lane <= NI;
+        pc = lane & 7, pcand = u32(lane) >> 3;
+        powner = pc <= NI;
+        spec = true, q_ok = false, qb0 = nullptr, q_key = 0, cur_vline = ~0u;
+        q0 = q1 = q2 = make_uint4(0, 0, 0, 0);
         stretch = st, squash = sq, nex16 = reinterpret_cast<const u16 *>(nx);
         u8 *p = smem_warp;
         int2 *tables = reinterpret_cast<int2 *>(p);
@@ -102,8 +115,8 @@ struct Chain {
             for (int k = lane; k < 256; k += 32) tables[i * 256 + k] = src[k];
         }
         ht = nullptr, ht_len = 16, sizebits = 0;
-        if (owner) {
-            const CompDesc &cd = M.comps[lane];
+        if (powner) {
+            const CompDesc &cd = M.comps[pc];
             ht = ws + cd.ht_off, ht_len = cd.ht_len, sizebits = cd.a + 2;
         }
         slot_at = nullptr;
@@ -122,7 +135,40 @@ struct Chain {
     // pr.reset() (predictor.v:827-833): contexts go to zero, history and tables stay.
     __device__ void segment_reset() {
         h = 0, mix_h = 0;
+        q_ok = false;  // requested with the old contexts
         stage_mix();
+    }
+
+    __device__ __forceinline__ u8 *slot_peek(u32 h0) const {
+        if (!md->paged) return ht + h0;
+        const u32 pte = reinterpret_cast<const u32 *>(ht)[h0 / kPageBytes];
+        return pte ? md->pool + u64(pte - 1u) * kPageBytes + (h0 & (kPageBytes - 1u)) : nullptr;
+    }
+
+    // After two bits of a nibble (c8part = c8 after them) the slot of the NEXT nibble is one of four:
+    // lane (pc, pcand) requests the three candidate slots of the line its completion would lead to.
+    // Loads only; the choice happens in probe().  Not the current slot's own line (it changes at the
+    // write-back), not an unmapped page.
+    __device__ __forceinline__ void probe_issue(u32 c8part) {
+        q_ok = false;
+        if (powner && spec) {
+            const u32 c8new = (c8part << 2) | pcand;
+            if (c8new < 256u) {
+                q_key = h + 16u * c8new;
+            } else {
+                u32 nh, mixv;
+                q_key = ctx_next(c8new & 255u, pc, nh, mixv) + 16u;
+            }
+            const u32 h0 = (q_key * 16u) & (ht_len - 16u);
+            u8 *b0 = slot_peek(h0);
+            if (b0 && (h0 >> 6) != cur_vline) {
+                qb0 = b0;
+                q0 = ldg128(b0);
+                q1 = ldg128(reinterpret_cast<u8 *>(reinterpret_cast<uintptr_t>(b0) ^ 16u));
+                q2 = ldg128(reinterpret_cast<u8 *>(reinterpret_cast<uintptr_t>(b0) ^ 32u));
+                q_ok = true;
+            }
+        }
     }
 
 
@@ -162,7 +208,7 @@ struct Chain {
     // After byte c: latch the hash of this lane's component (predictor.v:809-818).
     __device__ void byte_end(u32 c) {
         u32 nh, mixv;
-        h = ctx_next(c, lane, nh, mixv);
+        h = ctx_next(c, pc, nh, mixv);
         hist = nh;
         if (MIX2) {
             mix_h = mixv;
@@ -170,33 +216,53 @@ struct Chain {
         }
     }
 
-    // Predictor.find_ht for component `lane` (predictor.v:495-532).  The slot of the previous
-    // nibble goes back to its table first (the reference updates the table in place).
+    // Predictor.find_ht for every component (predictor.v:495-532).  The slot of the previous nibble
+    // goes back to its table first (the reference updates the table in place).  The choice is made by
+    // the candidate lane whose early request was right, else by the component's own lane with fresh
+    // loads; the chosen slot then travels to the component's lane by SHFL.
     __device__ __forceinline__ void probe(u32 c8v) {
-        if (owner) {
-            if (slot_at) *reinterpret_cast<uint4 *>(slot_at) = sl;
-            const u32 key = h + 16u * c8v;
+        if (owner && slot_at) *reinterpret_cast<uint4 *>(slot_at) = sl;
+        const u32 key = h + 16u * c8v;
+        const bool match = powner && q_ok && q_key == key;
+        const u32 grp = (__ballot_sync(kFull, match) >> pc) & 0x01010101u;
+        const bool actor = powner && (grp ? match : pcand == 0u);
+        const u32 h0 = (key * 16u) & (ht_len - 16u);
+        cur_vline = h0 >> 6;
+        uint4 nsl = make_uint4(0, 0, 0, 0);
+        u8 *nat = nullptr;
+        if (actor) {
             const u32 chk = (key >> sizebits) & 255u;
-            const u32 h0 = (key * 16u) & (ht_len - 16u);
-            // the three candidates h0, h0^16, h0^32 share one 64-byte line (and one page)
-            u8 *b0 = ht_slot(*md, ht, h0);
+            u8 *b0 = qb0;
+            uint4 s0 = q0, s1 = q1, s2 = q2;
+            if (!match) {
+                // All three candidates are requested before any is looked at and the choice is made
+                // with selects: as an if-chain the compiler serialises three HBM round trips.
+                b0 = ht_slot(*md, ht, h0);
+                asm volatile("" ::: "memory");  // after the write-back above
+                s0 = ldg128(b0);
+                s1 = ldg128(reinterpret_cast<u8 *>(reinterpret_cast<uintptr_t>(b0) ^ 16u));
+                s2 = ldg128(reinterpret_cast<u8 *>(reinterpret_cast<uintptr_t>(b0) ^ 32u));
+            }
             u8 *b1 = reinterpret_cast<u8 *>(reinterpret_cast<uintptr_t>(b0) ^ 16u);
             u8 *b2 = reinterpret_cast<u8 *>(reinterpret_cast<uintptr_t>(b0) ^ 32u);
-            // All three candidates are requested before any is looked at and the choice is made
-            // with selects: written as an if-chain the compiler makes the second and third load
-            // conditional, which serialises three HBM round trips.
-            const uint4 s0 = ldg128(b0), s1 = ldg128(b1), s2 = ldg128(b2);
             const bool m0 = (s0.x & 255u) == chk, m1 = (s1.x & 255u) == chk, m2 = (s2.x & 255u) == chk;
-            const u32 q0 = (s0.x >> 8) & 255u, q1 = (s1.x >> 8) & 255u, q2 = (s2.x >> 8) & 255u;
-            u8 *victim = (q0 <= q1 && q0 <= q2) ? b0 : (q1 < q2 ? b1 : b2);
+            const u32 p0 = (s0.x >> 8) & 255u, p1 = (s1.x >> 8) & 255u, p2 = (s2.x >> 8) & 255u;
+            u8 *victim = (p0 <= p1 && p0 <= p2) ? b0 : (p1 < p2 ? b1 : b2);
             const bool hit = m0 | m1 | m2;
-            slot_at = m0 ? b0 : m1 ? b1 : m2 ? b2 : victim;
-            uint4 pick = m0 ? s0 : (m1 ? s1 : s2);
-            sl.x = hit ? pick.x : chk;
-            sl.y = hit ? pick.y : 0u;
-            sl.z = hit ? pick.z : 0u;
-            sl.w = hit ? pick.w : 0u;
+            nat = m0 ? b0 : m1 ? b1 : m2 ? b2 : victim;
+            const uint4 pick = m0 ? s0 : (m1 ? s1 : s2);
+            nsl.x = hit ? pick.x : chk;
+            nsl.y = hit ? pick.y : 0u;
+            nsl.z = hit ? pick.z : 0u;
+            nsl.w = hit ? pick.w : 0u;
         }
+        q_ok = false;
+        // the acting lane of component pc: pc + 8 * (its candidate number), or pc itself
+        const int from = grp ? pc + ((__ffs(int(grp)) - 1) & ~7) : pc;
+        sl.x = __shfl_sync(kFull, nsl.x, from), sl.y = __shfl_sync(kFull, nsl.y, from);
+        sl.z = __shfl_sync(kFull, nsl.z, from), sl.w = __shfl_sync(kFull, nsl.w, from);
+        slot_at = reinterpret_cast<u8 *>(static_cast<uintptr_t>(
+            __shfl_sync(kFull, u64(reinterpret_cast<uintptr_t>(nat)), from)));
     }
 };
 
@@ -293,6 +359,7 @@ __device__ __forceinline__ u32 code_nibble(Chain<NI, MIX2> &C, u32 nib, u32 &c8,
         c8 = (c8 << 1) | y;
         idx = (idx * 2 + y) & 15u;
         got = (got << 1) | y;
+        if (DEC && k == 1) C.probe_issue(c8);
         if (MIX2) __syncwarp();  // the staged weight written by lane NI+1 may be re-read (mask < 255)
     }
     return got;
@@ -705,7 +772,7 @@ __global__ void __launch_bounds__(256, 1) k_decode_chain(DecodeArgs A) {
     C.setup(smem + kSharedTables + size_t(wic) * warp_smem_bytes(NI, MIX2), A.model, ws,
             reinterpret_cast<const int16_t *>(smem), reinterpret_cast<const u16 *>(smem + 65536),
             smem + 65536 + 8192);
-    if constexpr (TREE) C.spec = A.flags != 0;
+    C.spec = A.flags != 0;
     const DecBlock blk = A.blocks[bi];
     const u8 *arc = A.arc;
     u64 pos = blk.arc_pos;  // uniform across the warp

@@ -106,6 +106,8 @@ struct Ctx {
         }
         return sel < n_comp ? mine : 0u;
     }
+    // the history after byte c, without hashing
+    __device__ __forceinline__ u32 advance(u32 c) const { return mode == CTX_M1 ? (((hist << 8) | c) & 0xFFFFFFu) : c; }
 };
 
 }  // namespace
@@ -187,6 +189,8 @@ __global__ void __launch_bounds__(672, 1) k_encode_pipe3(EncodeArgs A, int block
         };
         // per-segment state
         u32 h = 0;                       // pr.reset(): contexts to zero (predictor.v:827-833)
+        u32 h1 = 0, h2 = 0;              // H: hashes of the next two bytes
+        bool h1_ok = false;
         u64 filled = 0;                  // H: plaintext ring holds [.., filled)
         i32 pprev[4] = {0, 0, 0, 0};     // M: this lane's predictions of the previous step
         u32 low = 1, high = 0xFFFFFFFFu; // C
@@ -205,8 +209,8 @@ __global__ void __launch_bounds__(672, 1) k_encode_pipe3(EncodeArgs A, int block
                     const i64 vb = N >> 1;
                     const u32 half = u32(N) & 1u;
                     if (half == 0) {
-                        const i64 at = vb - i64(pp);
-                        if (at >= 0 && filled < u64(at) + 64) {
+                        const i64 at = vb > i64(pp) ? vb - i64(pp) : 0;  // the PP byte is not in the ring
+                        if (filled < u64(at) + 64) {
                             __syncwarp();
 #pragma unroll
                             for (int k = 0; k < 4; ++k) {
@@ -217,16 +221,26 @@ __global__ void __launch_bounds__(672, 1) k_encode_pipe3(EncodeArgs A, int block
                             __syncwarp();
                         }
                         c = vbyte(vb);
+                        // Context hashes run two bytes ahead of the coding position, one evaluation per
+                        // byte: h = H(vb) is in use, h1 = H(vb+1) was computed a byte ago, h2 = H(vb+2)
+                        // is computed now (it needs byte vb+1, which the ring already holds).
+                        if (!h1_ok) {
+                            u32 nh;
+                            h1 = cx.next(c, lane, nh);
+                            h1_ok = true;
+                        }
+                        h2 = 0;
+                        if (vb + 1 < total) {
+                            Ctx ahead = cx;
+                            ahead.hist = cx.advance(c);
+                            u32 nh2;
+                            h2 = ahead.next(vbyte(vb + 1), lane, nh2);
+                        }
                         // the two lines byte vb+2 will touch are already determined: pull them into L2
                         // (two bytes of lead cover an HBM round trip even when this warp runs alone)
                         if (owner && !M.paged && vb + 2 < total) {
-                            u32 nh1, nh2;
-                            (void)cx.next(c, lane, nh1);
-                            Ctx ahead = cx;
-                            ahead.hist = nh1;
-                            const u32 hn = ahead.next(vbyte(vb + 1), lane, nh2);
                             const u32 c2 = vbyte(vb + 2);
-                            const u32 k0 = hn + 16u, k1 = hn + 16u * (16u | (c2 >> 4));
+                            const u32 k0 = h2 + 16u, k1 = h2 + 16u * (16u | (c2 >> 4));
                             prefetch_l2(ht + (((k0 * 16u) & (ht_len - 16u)) & ~63u));
                             prefetch_l2(ht + (((k1 * 16u) & (ht_len - 16u)) & ~63u));
                         }
@@ -234,8 +248,8 @@ __global__ void __launch_bounds__(672, 1) k_encode_pipe3(EncodeArgs A, int block
                     const u32 c8 = half ? (16u | (c >> 4)) : 1u;
                     const u32 nib = half ? (c & 15u) : (c >> 4);
                     // contexts of the next byte (predictor.v:809-818), needed one nibble early
-                    u32 h_next = h, hist_next = cx.hist;
-                    if (half == 1) h_next = cx.next(c, lane, hist_next);
+                    const u32 h_next = half ? h1 : h;
+                    const u32 hist_next = half ? cx.advance(c) : cx.hist;
                     if (owner) {
                         // Predictor.find_ht (predictor.v:495-532); the slot of the previous nibble goes
                         // back first (the reference updates the table in place)
@@ -289,6 +303,7 @@ __global__ void __launch_bounds__(672, 1) k_encode_pipe3(EncodeArgs A, int block
                         V.st_ring[(u32(N) & (kDepth - 1)) * (NI + 1) + lane] = st4;
                     }
                     h = h_next, cx.hist = hist_next;
+                    if (half == 1) h1 = h2;
                 }
             } else if (role == 1) {
                 // ================= M: ICM + ISSE stages, lane i lags i nibbles =================
