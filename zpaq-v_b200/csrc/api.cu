@@ -331,7 +331,7 @@ int run_compress(zpaqgpu_ctx *ctx, CompressJob &job) {
                     ea.in = job.d_in, ea.arena = static_cast<u8 *>(ctx->arena.p);
                     ea.blocks = d_blocks, ea.segs = d_esegs, ea.pay_len = static_cast<u64 *>(ctx->pay_len.p);
                     ea.order = d_order, ea.first_block = first, ea.n_blocks = n;
-                    ea.flags = std::getenv("ZPAQGPU_ENC_FLAGS") ? std::atoi(std::getenv("ZPAQGPU_ENC_FLAGS")) : 1;
+                    ea.flags = ctx->enc_l1_pull ? 1 : 0;
                     if (chain) {
                         if (!launch_encode_pipe3(m, ea, wpc, st)) {
                             ctx->err = "no chain kernel instantiation for this model";
@@ -866,6 +866,7 @@ int zpaqgpu_init(zpaqgpu_ctx **out, int device) {
     ctx->device = device;
     if (const char *v = std::getenv("ZPAQGPU_DECODER")) ctx->tree_decoder = std::strcmp(v, "serial") != 0;
     if (const char *v = std::getenv("ZPAQGPU_SPEC_PROBE")) ctx->spec_probe = std::atoi(v) != 0;
+    if (const char *v = std::getenv("ZPAQGPU_ENC_FLAGS")) ctx->enc_l1_pull = std::atoi(v) != 0;
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->sm_count = prop.multiProcessorCount;
     bool ok = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) == cudaSuccess &&

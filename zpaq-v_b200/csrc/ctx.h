@@ -38,7 +38,8 @@ struct zpaqgpu_ctx {
     void *tables_mem = nullptr;
     int kernel_pref = ZPAQGPU_KERNEL_AUTO;
     int table_mode = ZPAQGPU_TABLES_AUTO;
-    bool spec_probe = true;    // ZPAQGPU_SPEC_PROBE=0: the tree decoder probes only once a nibble is complete
+    bool enc_l1_pull = true;   // ZPAQGPU_ENC_FLAGS=0: the encoder's history warp does not pull the next slot line into L1
+    bool spec_probe = true;    // ZPAQGPU_SPEC_PROBE=0: the chain decoders probe only once a nibble is complete
     bool tree_decoder = true;  // ZPAQGPU_DECODER=serial in the environment selects the one-bit-at-a-time decoder
     zg::u64 ws_limit = 0;
     int sm_count = 148;
