@@ -37,6 +37,22 @@ def inputs():
     }
 
 
+JIDAC_DATE = 20260101120000
+JIDAC_OPTS = [dict(level=0, fragment=-1, dedup=False, block_bytes=0),
+              dict(level=0, fragment=0, dedup=True, block_bytes=0),
+              dict(level=1, fragment=2, dedup=True, block_bytes=16384),
+              dict(level=2, fragment=6, dedup=True, block_bytes=1 << 20),
+              dict(level=1, fragment=23, dedup=False, block_bytes=4096)]
+
+
+def jidac_tree():
+    ins = inputs()
+    t = datagen.text(150000, datagen.SEED0 + 77)
+    files = dict(ins)
+    files.update({"big.txt": t, "big-copy.txt": t, "mix": t[:50000] + ins["rand4k"] + t[50000:90000]})
+    return list(files), list(files.values())
+
+
 def main():
     out = {"provenance": "oracle/zpaq_oracle.c (parity unpinned against a V build; see make_golden.py)",
            "inputs": {}, "blocks": []}
@@ -53,6 +69,24 @@ def main():
     with open(os.path.join(HERE, "blocks.json"), "w") as f:
         json.dump(out, f, indent=1)
     print("wrote", len(out["blocks"]), "vectors")
+    # journaling archives (oracle/jidac_oracle.c): the reference's create_archive layout with the complete
+    # bytes of a tiny tree, and hashes + fragment tables for the fragmentation / dedup option sets
+    jd = {"provenance": "oracle/jidac_oracle.c: archive layout pinned by jidac.v:47-296; fragmentation rule "
+                        "(fragment >= 0) is upstream zpaq's, parity unpinned",
+          "date": JIDAC_DATE, "archives": []}
+    names, files = jidac_tree()
+    tiny = {"a": b"hello world", "empty": b""}
+    jd["tiny_reference_hex"] = ob.jidac_add(list(tiny), list(tiny.values()), JIDAC_DATE).hex()
+    for opt in JIDAC_OPTS:
+        arc = ob.jidac_add(names, files, JIDAC_DATE, **opt)
+        frs, stored = ob.jidac_fragment(files, opt["fragment"], opt["dedup"])
+        jd["archives"].append({"opts": opt, "len": len(arc), "sha1": hashlib.sha1(arc).hexdigest(),
+                               "n_fragments": len(frs), "n_stored": stored,
+                               "cuts_sha1": hashlib.sha1(b"".join(b"%d,%d,%d;" % (f["off"], f["len"], f["id"])
+                                                                   for f in frs)).hexdigest()})
+    with open(os.path.join(HERE, "jidac.json"), "w") as f:
+        json.dump(jd, f, indent=1)
+    print("wrote", len(jd["archives"]), "jidac vectors")
 
 
 if __name__ == "__main__":

@@ -54,3 +54,48 @@ def test_gpu_reproduces_golden(gpu_ctx, kernel):
     finally:
         gpu_ctx.set_kernel(0)
         gpu_ctx.set_workspace_limit(0)
+
+
+def load_jidac():
+    import sys
+    sys.path.insert(0, os.path.join(HERE, "golden"))
+    import make_golden
+    with open(os.path.join(HERE, "golden", "jidac.json")) as f:
+        gold = json.load(f)
+    return gold, make_golden
+
+
+def _cuts_sha1(frs):
+    return hashlib.sha1(b"".join(b"%d,%d,%d;" % (f["off"], f["len"], f["id"]) for f in frs)).hexdigest()
+
+
+def test_oracle_reproduces_jidac_golden():
+    gold, mg = load_jidac()
+    names, files = mg.jidac_tree()
+    tiny = {"a": b"hello world", "empty": b""}
+    assert ob.jidac_add(list(tiny), list(tiny.values()), gold["date"]).hex() == gold["tiny_reference_hex"]
+    assert len(gold["archives"]) == len(mg.JIDAC_OPTS)
+    for rec in gold["archives"]:
+        arc = ob.jidac_add(names, files, gold["date"], **rec["opts"])
+        assert len(arc) == rec["len"] and hashlib.sha1(arc).hexdigest() == rec["sha1"], rec["opts"]
+        frs, stored = ob.jidac_fragment(files, rec["opts"]["fragment"], rec["opts"]["dedup"])
+        assert (len(frs), stored, _cuts_sha1(frs)) == (rec["n_fragments"], rec["n_stored"], rec["cuts_sha1"])
+
+
+@pytest.mark.gpu
+def test_gpu_reproduces_jidac_golden(gpu_ctx):
+    gold, mg = load_jidac()
+    names, files = mg.jidac_tree()
+    tiny = {"a": b"hello world", "empty": b""}
+    assert gpu_ctx.jidac_add(list(tiny), list(tiny.values()), gold["date"]).hex() == gold["tiny_reference_hex"]
+    gpu_ctx.set_workspace_limit(8 << 30)
+    try:
+        for rec in gold["archives"]:
+            arc = gpu_ctx.jidac_add(names, files, gold["date"], **rec["opts"])
+            assert len(arc) == rec["len"] and hashlib.sha1(arc).hexdigest() == rec["sha1"], rec["opts"]
+            frs, stored = gpu_ctx.jidac_fragment(files, rec["opts"]["fragment"], rec["opts"]["dedup"])
+            assert (len(frs), stored, _cuts_sha1(frs)) == (rec["n_fragments"], rec["n_stored"], rec["cuts_sha1"])
+            back = {r["name"]: r["data"] for r in gpu_ctx.jidac_extract(arc)}
+            assert back == dict(zip(names, files))
+    finally:
+        gpu_ctx.set_workspace_limit(0)
