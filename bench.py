@@ -214,8 +214,20 @@ def main():
     if world > 1:
         import torch.distributed as dist_
         dist = dist_
-        os.environ["NCCL_DEBUG"] = "WARN"  # rank 0 prints ONE JSON line on stdout: no NCCL version banner
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        # rank 0 prints ONE JSON line on stdout: NCCL's version banner (printed by the library when the
+        # first communicator comes up) is kept off fd 1
+        os.environ["NCCL_DEBUG"] = "WARN"
+        sys.stdout.flush()
+        saved, null = os.dup(1), os.open(os.devnull, os.O_WRONLY)
+        os.dup2(null, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            os.dup2(saved, 1)
+            os.close(saved)
+            os.close(null)
 
     level, nb, bb = args.level, args.blocks, args.block_kib * 1024
     total = nb * bb
