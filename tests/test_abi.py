@@ -84,3 +84,35 @@ def test_product_does_not_import_oracle():
                     if re.search(r"zpaq_oracle|oracle_binding|oracle/", text):
                         bad.append(os.path.join(dirpath, f))
     assert not bad, bad
+
+
+def test_ctypes_structs_match_the_header(tmp_path):
+    """sizeof / offsetof of every public struct as gcc sees include/zpaqgpu.h against the ctypes mirrors."""
+    import ctypes as C
+    import subprocess
+    from zpaq_v_b200 import binding as zb
+    structs = {"zpaqgpu_model_info": zb.ModelInfo, "zpaqgpu_segment": zb.Segment, "zpaqgpu_stats": zb.Stats,
+               "zpaqgpu_jidac_opts": zb.JidacOpts, "zpaqgpu_fragment": zb.Fragment, "zpaqgpu_jidac_file": zb.JidacFile,
+               "zpaqgpu_jidac_stats": zb.JidacStats}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "zpaqgpu.h"', 'int main(void) {']
+    for cname, cls in structs.items():
+        lines.append('printf("%s %%zu", sizeof(%s));' % (cname, cname))
+        for field, _ in cls._fields_:
+            lines.append('printf(" %%zu", offsetof(%s, %s));' % (cname, field))
+        lines.append('printf("\\n");')
+    lines += ['return 0;', '}']
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = str(tmp_path / "layout")
+    subprocess.check_call(["gcc", "-I" + os.path.join(ROOT, "include"), str(src), "-o", exe])
+    out = subprocess.check_output([exe]).decode().strip().splitlines()
+    assert len(out) == len(structs)
+    for line, (cname, cls) in zip(out, structs.items()):
+        parts = line.split()
+        assert parts[0] == cname
+        nums = [int(x) for x in parts[1:]]
+        assert nums[0] == C.sizeof(cls), cname
+        assert nums[1:] == [getattr(cls, f).offset for f, _ in cls._fields_], cname
+    # the oracle's fragment record is copied into the same layout by the tests
+    import oracle_binding as ob
+    assert C.sizeof(ob._Frag) == C.sizeof(zb.Fragment)
