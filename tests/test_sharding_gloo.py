@@ -1,7 +1,7 @@
 """world_size-2 gloo test of the multi-GPU host logic: disjoint block ranges per
 rank, no data-path collective, host concatenation in block order equals the single-process archive.
 The per-rank coder is the CPU oracle here (no GPU in this container); on the GPU box the same
-functions are driven with Context.compress_blocks (tests/test_gpu_multi.py)."""
+functions are driven with Context.compress_blocks and Context.jidac_fragment (tests/test_gpu_multi.py)."""
 import os
 import sys
 
