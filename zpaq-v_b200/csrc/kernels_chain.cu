@@ -47,81 +47,57 @@ __device__ __forceinline__ uint4 ldg128(const u8 *p) {
     return v;
 }
 
+// State and steps both chain decoders share: the closed-form context hashes, the staged MIX2
+// weights, and the probing role.  For probing, lane = (component pc = lane & 7, candidate
+// pcand = lane >> 3): the four lanes of a component hold its table geometry and context hash, request
+// the four possible slot lines of the next nibble two bits early (probe_issue) and make the find_ht
+// choice (choose) from registers when their guess was right.
 template <int NI, bool MIX2>
-struct Chain {
+struct ProbeBase {
     // shared-memory views
     const int16_t *stretch;  // padded: entry 0 holds entry 1
     const u16 *squash;       // padded: indexed by p + 2048
-    const u16 *nex16;  // nex16[s] = next(s,0) | next(s,1) << 8
-    int2 *tab;         // this lane's table: ICM {cm[s], stretch(cm[s]>>8)} or ISSE {wt0, wt1}
-    int2 *dump;        // 32 entries nobody reads
+    const u16 *nex16;        // nex16[s] = next(s,0) | next(s,1) << 8
     u16 *a16s;
     u8 *ring;
     u8 *stage;
-    // per lane: the hash table of component `lane`, its parked slot and context hash
-    u8 *ht;            // hash table (dense) or its page table (paged)
+    int lane;
+    // hash table of component pc (dense) or its page table (paged), and its context hash
+    const ModelDev *md;
+    u8 *ht;
     u32 ht_len;
     int sizebits;
-    u8 *slot_at;       // where the parked slot lives in HBM (nullptr: none yet)
-    uint4 sl;
-    const ModelDev *md;
     u32 h;
-    bool owner;        // lane <= NI
+    int pc;
+    u32 pcand;
+    bool powner;             // pc <= NI
     // MIX2
     u16 *a16;
     u32 a16_mask, mix_h, mix_sel;
     i32 mix_rate;
     // context history (uniform)
     int ctx_mode, n_hash, n_comp;
-    u32 hist;          // CTX_M1: previous three bytes; CTX_HASHCHAIN: previous byte
-    int lane;
-    // Probing role (speculative probe, as in the tree decoder): lane = (component pc = lane & 7,
-    // candidate pcand = lane >> 3).  Lanes 0..NI are candidate 0 of their own component.
-    int pc;
-    u32 pcand;
-    bool powner, spec;
-    uint4 q0, q1, q2;  // candidate slots of the NEXT nibble, requested two bits early
+    u32 hist;                // CTX_M1: previous three bytes; CTX_HASHCHAIN: previous byte
+    // candidate slots of the NEXT nibble, requested two bits before its context is known
+    uint4 q0, q1, q2;
     u8 *qb0;
-    u32 q_key, cur_vline;
-    bool q_ok;
+    u32 q_key, cur_vline;    // cur_vline: 64-byte line (virtual offset >> 6) of the current slot
+    bool q_ok, spec;
 
-    __device__ void setup(u8 *smem_warp, const ModelDev &M, u8 *ws, const int16_t *st, const u16 *sq,
-                          const u8 *nx) {
+    __device__ void base_setup(const ModelDev &M, u8 *ws, const int16_t *st, const u16 *sq, const u8 *nx) {
         lane = threadIdx.x & 31;
-        owner = lane <= NI;
         pc = lane & 7, pcand = u32(lane) >> 3;
         powner = pc <= NI;
         spec = true, q_ok = false, qb0 = nullptr, q_key = 0, cur_vline = ~0u;
         q0 = q1 = q2 = make_uint4(0, 0, 0, 0);
         stretch = st, squash = sq, nex16 = reinterpret_cast<const u16 *>(nx);
-        u8 *p = smem_warp;
-        int2 *tables = reinterpret_cast<int2 *>(p);
-        p += size_t(NI + 1) * 2048;
-        dump = reinterpret_cast<int2 *>(p), p += 256;
-        a16s = reinterpret_cast<u16 *>(p), p += MIX2 ? 512 : 0;
-        ring = p, p += kRing;
-        stage = p;
-        tab = tables + (owner ? lane : 0) * 256;
         ctx_mode = M.ctx_mode, n_hash = M.n_hash, n_comp = M.n;
-        // adaptive tables: the fill kernel wrote their initial images into the workspace
-        const u32 *src0 = reinterpret_cast<const u32 *>(ws + M.comps[0].cm_off);
-        for (int k = lane; k < 256; k += 32) {
-            const u32 v = src0[k];
-            tables[k] = make_int2(i32(v), i32(st[d_stretch_pad_idx(v >> 8)]));
-        }
-#pragma unroll
-        for (int i = 1; i <= NI; ++i) {
-            const int2 *src = reinterpret_cast<const int2 *>(ws + M.comps[i].cm_off);
-            for (int k = lane; k < 256; k += 32) tables[i * 256 + k] = src[k];
-        }
         ht = nullptr, ht_len = 16, sizebits = 0;
         if (powner) {
             const CompDesc &cd = M.comps[pc];
             ht = ws + cd.ht_off, ht_len = cd.ht_len, sizebits = cd.a + 2;
         }
-        slot_at = nullptr;
         md = &M;
-        sl = make_uint4(0, 0, 0, 0);
         h = 0, hist = 0, mix_h = 0;
         a16 = nullptr, a16_mask = 0, mix_sel = 0, mix_rate = 0;
         if (MIX2) {
@@ -129,7 +105,20 @@ struct Chain {
             a16 = reinterpret_cast<u16 *>(ws + cd.a16_off);
             a16_mask = cd.a16_len - 1, mix_sel = cd.p[3], mix_rate = i32(cd.p[2]);
         }
-        __syncwarp();
+    }
+
+    // adaptive tables into shared memory: the fill kernel wrote their initial images into the workspace
+    __device__ void load_tables(int2 *tables, const ModelDev &M, const u8 *ws) {
+        const u32 *src0 = reinterpret_cast<const u32 *>(ws + M.comps[0].cm_off);
+        for (int k = lane; k < 256; k += 32) {
+            const u32 v = src0[k];
+            tables[k] = make_int2(i32(v), i32(stretch[d_stretch_pad_idx(v >> 8)]));
+        }
+#pragma unroll
+        for (int i = 1; i <= NI; ++i) {
+            const int2 *src = reinterpret_cast<const int2 *>(ws + M.comps[i].cm_off);
+            for (int k = lane; k < 256; k += 32) tables[i * 256 + k] = src[k];
+        }
     }
 
     // pr.reset() (predictor.v:827-833): contexts go to zero, history and tables stay.
@@ -138,39 +127,6 @@ struct Chain {
         q_ok = false;  // requested with the old contexts
         stage_mix();
     }
-
-    __device__ __forceinline__ u8 *slot_peek(u32 h0) const {
-        if (!md->paged) return ht + h0;
-        const u32 pte = reinterpret_cast<const u32 *>(ht)[h0 / kPageBytes];
-        return pte ? md->pool + u64(pte - 1u) * kPageBytes + (h0 & (kPageBytes - 1u)) : nullptr;
-    }
-
-    // After two bits of a nibble (c8part = c8 after them) the slot of the NEXT nibble is one of four:
-    // lane (pc, pcand) requests the three candidate slots of the line its completion would lead to.
-    // Loads only; the choice happens in probe().  Not the current slot's own line (it changes at the
-    // write-back), not an unmapped page.
-    __device__ __forceinline__ void probe_issue(u32 c8part) {
-        q_ok = false;
-        if (powner && spec) {
-            const u32 c8new = (c8part << 2) | pcand;
-            if (c8new < 256u) {
-                q_key = h + 16u * c8new;
-            } else {
-                u32 nh, mixv;
-                q_key = ctx_next(c8new & 255u, pc, nh, mixv) + 16u;
-            }
-            const u32 h0 = (q_key * 16u) & (ht_len - 16u);
-            u8 *b0 = slot_peek(h0);
-            if (b0 && (h0 >> 6) != cur_vline) {
-                qb0 = b0;
-                q0 = ldg128(b0);
-                q1 = ldg128(reinterpret_cast<u8 *>(reinterpret_cast<uintptr_t>(b0) ^ 16u));
-                q2 = ldg128(reinterpret_cast<u8 *>(reinterpret_cast<uintptr_t>(b0) ^ 32u));
-                q_ok = true;
-            }
-        }
-    }
-
 
     __device__ void stage_mix() {
         if (MIX2) {
@@ -205,7 +161,7 @@ struct Chain {
         return sel < n_comp ? mine : 0u;
     }
 
-    // After byte c: latch the hash of this lane's component (predictor.v:809-818).
+    // After byte c: latch the hash of component pc (predictor.v:809-818).
     __device__ void byte_end(u32 c) {
         u32 nh, mixv;
         h = ctx_next(c, pc, nh, mixv);
@@ -216,21 +172,54 @@ struct Chain {
         }
     }
 
-    // Predictor.find_ht for every component (predictor.v:495-532).  The slot of the previous nibble
-    // goes back to its table first (the reference updates the table in place).  The choice is made by
-    // the candidate lane whose early request was right, else by the component's own lane with fresh
-    // loads; the chosen slot then travels to the component's lane by SHFL.
-    __device__ __forceinline__ void probe(u32 c8v) {
-        if (owner && slot_at) *reinterpret_cast<uint4 *>(slot_at) = sl;
+    // Address of a slot without side effects: nullptr when a paged table has no page there yet.
+    __device__ __forceinline__ u8 *slot_peek(u32 h0) const {
+        if (!md->paged) return ht + h0;
+        const u32 pte = reinterpret_cast<const u32 *>(ht)[h0 / kPageBytes];
+        return pte ? md->pool + u64(pte - 1u) * kPageBytes + (h0 & (kPageBytes - 1u)) : nullptr;
+    }
+
+    // Called when the first two bits of a nibble are decoded (c8part = c8 after them).  The slot the
+    // NEXT nibble probes is then one of four; lane (pc, pcand) requests the three candidate slots of
+    // the line its completion pcand would lead to, so the HBM/L2 round trip runs under the rest of the
+    // nibble, the table updates and the per-byte bookkeeping instead of after them.  Loads only: the
+    // choice (and any eviction) happens in choose().  A line that is the current slot's own line is
+    // not requested (it changes at the write-back), nor an unmapped page.
+    __device__ __forceinline__ void probe_issue(u32 c8part) {
+        q_ok = false;
+        if (powner && spec) {
+            const u32 c8new = (c8part << 2) | pcand;
+            if (c8new < 256u) {
+                q_key = h + 16u * c8new;            // low nibble of the same byte
+            } else {
+                u32 nh, mixv;                       // high nibble of the next byte (predictor.v:809-818)
+                q_key = ctx_next(c8new & 255u, pc, nh, mixv) + 16u;
+            }
+            const u32 h0 = (q_key * 16u) & (ht_len - 16u);
+            u8 *b0 = slot_peek(h0);
+            if (b0 && (h0 >> 6) != cur_vline) {
+                qb0 = b0;
+                q0 = ldg128(b0);
+                q1 = ldg128(reinterpret_cast<u8 *>(reinterpret_cast<uintptr_t>(b0) ^ 16u));
+                q2 = ldg128(reinterpret_cast<u8 *>(reinterpret_cast<uintptr_t>(b0) ^ 32u));
+                q_ok = true;
+            }
+        }
+    }
+
+    // Predictor.find_ht of component pc (predictor.v:495-532) for the nibble that starts with c8v.
+    // Returns true on the acting lane of each component -- the lane whose early request was the right
+    // one, else candidate lane 0, which loads now -- with the chosen slot and its address; `grp` has
+    // bit 8k set when candidate lane k of this component acts.  Must run after the write-back of the
+    // previous slot.
+    __device__ __forceinline__ bool choose(u32 c8v, uint4 &chosen, u8 *&at, u32 &grp) {
         const u32 key = h + 16u * c8v;
         const bool match = powner && q_ok && q_key == key;
-        const u32 grp = (__ballot_sync(kFull, match) >> pc) & 0x01010101u;
-        const bool actor = powner && (grp ? match : pcand == 0u);
+        grp = (__ballot_sync(kFull, match) >> pc) & 0x01010101u;
+        const bool acting = powner && (grp ? match : pcand == 0u);
         const u32 h0 = (key * 16u) & (ht_len - 16u);
         cur_vline = h0 >> 6;
-        uint4 nsl = make_uint4(0, 0, 0, 0);
-        u8 *nat = nullptr;
-        if (actor) {
+        if (acting) {
             const u32 chk = (key >> sizebits) & 255u;
             u8 *b0 = qb0;
             uint4 s0 = q0, s1 = q1, s2 = q2;
@@ -238,7 +227,7 @@ struct Chain {
                 // All three candidates are requested before any is looked at and the choice is made
                 // with selects: as an if-chain the compiler serialises three HBM round trips.
                 b0 = ht_slot(*md, ht, h0);
-                asm volatile("" ::: "memory");  // after the write-back above
+                asm volatile("" ::: "memory");  // after the write-back of the previous slot
                 s0 = ldg128(b0);
                 s1 = ldg128(reinterpret_cast<u8 *>(reinterpret_cast<uintptr_t>(b0) ^ 16u));
                 s2 = ldg128(reinterpret_cast<u8 *>(reinterpret_cast<uintptr_t>(b0) ^ 32u));
@@ -249,16 +238,57 @@ struct Chain {
             const u32 p0 = (s0.x >> 8) & 255u, p1 = (s1.x >> 8) & 255u, p2 = (s2.x >> 8) & 255u;
             u8 *victim = (p0 <= p1 && p0 <= p2) ? b0 : (p1 < p2 ? b1 : b2);
             const bool hit = m0 | m1 | m2;
-            nat = m0 ? b0 : m1 ? b1 : m2 ? b2 : victim;
+            at = m0 ? b0 : m1 ? b1 : m2 ? b2 : victim;
             const uint4 pick = m0 ? s0 : (m1 ? s1 : s2);
-            nsl.x = hit ? pick.x : chk;
-            nsl.y = hit ? pick.y : 0u;
-            nsl.z = hit ? pick.z : 0u;
-            nsl.w = hit ? pick.w : 0u;
+            chosen.x = hit ? pick.x : chk;
+            chosen.y = hit ? pick.y : 0u;
+            chosen.z = hit ? pick.z : 0u;
+            chosen.w = hit ? pick.w : 0u;
         }
         q_ok = false;
+        return acting;
+    }
+};
+
+// Serial decoder state: one model component per lane (lane i = component i, i <= NI).
+template <int NI, bool MIX2>
+struct Chain : ProbeBase<NI, MIX2> {
+    using B = ProbeBase<NI, MIX2>;
+    int2 *tab;         // this lane's table: ICM {cm[s], stretch(cm[s]>>8)} or ISSE {wt0, wt1}
+    int2 *dump;        // 32 entries nobody reads
+    u8 *slot_at;       // where the parked slot lives in HBM (nullptr: none yet)
+    uint4 sl;          // the hash slot of component `lane` for the current nibble
+    bool owner;        // lane <= NI
+
+    __device__ void setup(u8 *smem_warp, const ModelDev &M, u8 *ws, const int16_t *st, const u16 *sq,
+                          const u8 *nx) {
+        B::base_setup(M, ws, st, sq, nx);
+        owner = B::lane <= NI;
+        u8 *p = smem_warp;
+        int2 *tables = reinterpret_cast<int2 *>(p);
+        p += size_t(NI + 1) * 2048;
+        dump = reinterpret_cast<int2 *>(p), p += 256;
+        B::a16s = reinterpret_cast<u16 *>(p), p += MIX2 ? 512 : 0;
+        B::ring = p, p += kRing;
+        B::stage = p;
+        tab = tables + (owner ? B::lane : 0) * 256;
+        B::load_tables(tables, M, ws);
+        slot_at = nullptr;
+        sl = make_uint4(0, 0, 0, 0);
+        __syncwarp();
+    }
+
+    // Predictor.find_ht for every component.  The slot of the previous nibble goes back to its table
+    // first (the reference updates the table in place); the chosen slot then travels from the acting
+    // lane to the component's own lane by SHFL.
+    __device__ __forceinline__ void probe(u32 c8v) {
+        if (owner && slot_at) *reinterpret_cast<uint4 *>(slot_at) = sl;
+        uint4 nsl = make_uint4(0, 0, 0, 0);
+        u8 *nat = nullptr;
+        u32 grp;
+        B::choose(c8v, nsl, nat, grp);
         // the acting lane of component pc: pc + 8 * (its candidate number), or pc itself
-        const int from = grp ? pc + ((__ffs(int(grp)) - 1) & ~7) : pc;
+        const int from = grp ? B::pc + ((__ffs(int(grp)) - 1) & ~7) : B::pc;
         sl.x = __shfl_sync(kFull, nsl.x, from), sl.y = __shfl_sync(kFull, nsl.y, from);
         sl.z = __shfl_sync(kFull, nsl.z, from), sl.w = __shfl_sync(kFull, nsl.w, from);
         slot_at = reinterpret_cast<u8 *>(static_cast<uintptr_t>(
@@ -382,48 +412,22 @@ __device__ __forceinline__ u32 code_nibble(Chain<NI, MIX2> &C, u32 nib, u32 &c8,
 // evaluation (predictor.v:536-824): same table reads, same updates, in the same order.
 // ------------------------------------------------------------------------------------------
 template <int NI, bool MIX2>
-struct Tree {
+struct Tree : ProbeBase<NI, MIX2> {
+    using B = ProbeBase<NI, MIX2>;
     static constexpr int NC = NI + 1;
-    const int16_t *stretch;
-    const u16 *squash;
-    const u16 *nex16;
     int2 *tabs;        // NC tables of 256 entries: ICM {cm, stretch(cm>>8)}, ISSE {wt0, wt1}
     u8 *slots;         // NC x 16 bytes: the hash slots of the current nibble
-    u16 *a16s;
-    u8 *ring;
-    u8 *stage;
-    // Probing role: lane = (component pc = lane & 7, candidate pcand = lane >> 3).  The four lanes of a
-    // component hold its table geometry, context hash and current slot address; see probe_issue().
-    u8 *ht;
-    u32 ht_len;
-    int sizebits;
-    u8 *slot_at;
-    const ModelDev *md;
-    u32 h;
-    bool owner;        // pc < NC
-    int pc;
-    u32 pcand;
-    u16 *a16;
-    u32 a16_mask, mix_h, mix_sel;
-    i32 mix_rate;
-    int ctx_mode, n_hash, n_comp;
-    u32 hist;
-    int lane;
+    u8 *slot_at;       // acting lanes: where the current slot of component pc lives in HBM
+    bool actor;        // this lane made the choice of the current nibble and writes the slot back
     // tree geometry of this lane
     u32 node, yy;
     int depth;
     int src[3];        // lane whose prepared update reaches this node after round l (self when none does)
-    // candidate slots of the NEXT nibble, requested two bits before its context is known
-    uint4 q0, q1, q2;
-    u8 *qb0;
-    u32 q_key, cur_vline;   // cur_vline: 64-byte line (virtual offset >> 6) of the current slot
-    bool q_ok, actor, spec;
 
     __device__ void setup(u8 *smem_warp, const ModelDev &M, u8 *ws, const int16_t *st, const u16 *sq,
                           const u8 *nx) {
-        lane = threadIdx.x & 31;
-        pc = lane & 7, pcand = u32(lane) >> 3;
-        owner = pc <= NI;
+        B::base_setup(M, ws, st, sq, nx);
+        const int lane = B::lane;
         node = u32(lane) & 15u, yy = u32(lane) >> 4;
         depth = 31 - __clz(int(node | 1u));
 #pragma unroll
@@ -434,165 +438,26 @@ struct Tree {
                 src[l] = int(anc + 16u * bit);
             }
         }
-        stretch = st, squash = sq, nex16 = reinterpret_cast<const u16 *>(nx);
         u8 *p = smem_warp;
         tabs = reinterpret_cast<int2 *>(p);
         p += size_t(NC) * 2048;
         slots = p, p += 256;
-        a16s = reinterpret_cast<u16 *>(p), p += MIX2 ? 512 : 0;
-        ring = p, p += kRing;
-        stage = p;
-        ctx_mode = M.ctx_mode, n_hash = M.n_hash, n_comp = M.n;
-        const u32 *src0 = reinterpret_cast<const u32 *>(ws + M.comps[0].cm_off);
-        for (int k = lane; k < 256; k += 32) {
-            const u32 v = src0[k];
-            tabs[k] = make_int2(i32(v), i32(st[d_stretch_pad_idx(v >> 8)]));
-        }
-#pragma unroll
-        for (int i = 1; i <= NI; ++i) {
-            const int2 *srci = reinterpret_cast<const int2 *>(ws + M.comps[i].cm_off);
-            for (int k = lane; k < 256; k += 32) tabs[i * 256 + k] = srci[k];
-        }
+        B::a16s = reinterpret_cast<u16 *>(p), p += MIX2 ? 512 : 0;
+        B::ring = p, p += kRing;
+        B::stage = p;
+        B::load_tables(tabs, M, ws);
         for (int k = lane; k < 64; k += 32) reinterpret_cast<u32 *>(slots)[k] = 0;
-        ht = nullptr, ht_len = 16, sizebits = 0;
-        if (owner) {
-            const CompDesc &cd = M.comps[pc];
-            ht = ws + cd.ht_off, ht_len = cd.ht_len, sizebits = cd.a + 2;
-        }
-        slot_at = nullptr;
-        md = &M;
-        h = 0, hist = 0, mix_h = 0;
-        q_ok = false, qb0 = nullptr, q_key = 0, cur_vline = ~0u, actor = false, spec = true;
-        q0 = q1 = q2 = make_uint4(0, 0, 0, 0);
-        a16 = nullptr, a16_mask = 0, mix_sel = 0, mix_rate = 0;
-        if (MIX2) {
-            const CompDesc &cd = M.comps[NI + 1];
-            a16 = reinterpret_cast<u16 *>(ws + cd.a16_off);
-            a16_mask = cd.a16_len - 1, mix_sel = cd.p[3], mix_rate = i32(cd.p[2]);
-        }
+        slot_at = nullptr, actor = false;
         __syncwarp();
     }
 
-    __device__ void segment_reset() {
-        h = 0, mix_h = 0;
-        q_ok = false;  // requested with the old contexts
-        stage_mix();
-    }
-
-    // Address of a slot without side effects: nullptr when a paged table has no page there yet.
-    __device__ __forceinline__ u8 *slot_peek(u32 h0) const {
-        if (!md->paged) return ht + h0;
-        const u32 pte = reinterpret_cast<const u32 *>(ht)[h0 / kPageBytes];
-        return pte ? md->pool + u64(pte - 1u) * kPageBytes + (h0 & (kPageBytes - 1u)) : nullptr;
-    }
-
-    // Called when the first two bits of a nibble are decoded (c8part = c8 after them).  The slot the
-    // NEXT nibble probes is then one of four; lane (pc, pcand) requests the three candidate slots of
-    // the line its completion pcand would lead to, so the HBM/L2 round trip runs under the remaining
-    // two tree rounds, the table updates and the per-byte bookkeeping instead of after them.  Loads
-    // only: the choice (and any eviction) happens in probe().  A line that is the current slot's own
-    // line is not requested: it changes at the write-back.
-    __device__ __forceinline__ void probe_issue(u32 c8part) {
-        q_ok = false;
-        if (owner && spec) {
-            const u32 c8new = (c8part << 2) | pcand;
-            if (c8new < 256u) {
-                q_key = h + 16u * c8new;            // low nibble of the same byte
-            } else {
-                u32 nh, mixv;                       // high nibble of the next byte (predictor.v:809-818)
-                q_key = ctx_next(c8new & 255u, pc, nh, mixv) + 16u;
-            }
-            const u32 h0 = (q_key * 16u) & (ht_len - 16u);
-            u8 *b0 = slot_peek(h0);
-            if (b0 && (h0 >> 6) != cur_vline) {
-                qb0 = b0;
-                q0 = ldg128(b0);
-                q1 = ldg128(reinterpret_cast<u8 *>(reinterpret_cast<uintptr_t>(b0) ^ 16u));
-                q2 = ldg128(reinterpret_cast<u8 *>(reinterpret_cast<uintptr_t>(b0) ^ 32u));
-                q_ok = true;
-            }
-        }
-    }
-
-    __device__ void stage_mix() {
-        if (MIX2) {
-            __syncwarp();
-            for (int k = lane; k < 256; k += 32) a16s[k] = a16[(mix_h + u32(k)) & a16_mask];
-            __syncwarp();
-        }
-    }
-
-    __device__ __forceinline__ u32 ctx_next(u32 c, int sel, u32 &new_hist, u32 &mixv) const {
-        u32 mine = 0;
-        mixv = 0;
-        if (ctx_mode == CTX_M1) {
-            u32 a = (0u + c + 512u) * 773u;
-            a = (a + (hist & 255u) + 512u) * 773u;
-            const u32 h0 = a;
-            a = (a + ((hist >> 8) & 255u) + 512u) * 773u;
-            a = (a + ((hist >> 16) & 255u) + 512u) * 773u;
-            mine = sel == 0 ? h0 : (sel == 1 ? a : 0u);
-            new_hist = ((hist << 8) | c) & 0xFFFFFFu;
-        } else {
-            u32 a = c;
-            for (int r = 0; r < n_hash; ++r) {
-                a = (a + hist + 512u) * 773u;
-                if (r == sel) mine = a;
-                if (MIX2 && r == NI + 1) mixv = a;
-            }
-            new_hist = c;
-        }
-        return sel < n_comp ? mine : 0u;
-    }
-
-    __device__ void byte_end(u32 c) {
-        u32 nh, mixv;
-        h = ctx_next(c, pc, nh, mixv);
-        hist = nh;
-        if (MIX2) {
-            mix_h = mixv;
-            stage_mix();
-        }
-    }
-
-    // Predictor.find_ht of every component (predictor.v:495-532).  For each component the lane whose
-    // early request turned out to be the right one makes the choice from its registers; when there is
-    // none (first nibble of a segment, own-line hazard, unmapped page) candidate lane 0 loads now.
-    // The chosen slot and its address are published to the warp through shared memory.
+    // Predictor.find_ht of every component; the acting lane publishes the chosen slot to the warp
+    // through shared memory and keeps its address for the write-back at the end of the nibble.
     __device__ __forceinline__ void probe(u32 c8v) {
-        const u32 key = h + 16u * c8v;
-        const bool match = owner && q_ok && q_key == key;
-        const u32 grp = (__ballot_sync(kFull, match) >> pc) & 0x01010101u;
-        actor = owner && (grp ? match : pcand == 0u);
-        const u32 h0 = (key * 16u) & (ht_len - 16u);
-        cur_vline = h0 >> 6;
-        if (actor) {
-            const u32 chk = (key >> sizebits) & 255u;
-            u8 *b0 = qb0;
-            uint4 s0 = q0, s1 = q1, s2 = q2;
-            if (!match) {
-                b0 = ht_slot(*md, ht, h0);
-                asm volatile("" ::: "memory");  // after the write-back of the previous slot
-                s0 = ldg128(b0);
-                s1 = ldg128(reinterpret_cast<u8 *>(reinterpret_cast<uintptr_t>(b0) ^ 16u));
-                s2 = ldg128(reinterpret_cast<u8 *>(reinterpret_cast<uintptr_t>(b0) ^ 32u));
-            }
-            u8 *b1 = reinterpret_cast<u8 *>(reinterpret_cast<uintptr_t>(b0) ^ 16u);
-            u8 *b2 = reinterpret_cast<u8 *>(reinterpret_cast<uintptr_t>(b0) ^ 32u);
-            const bool m0 = (s0.x & 255u) == chk, m1 = (s1.x & 255u) == chk, m2 = (s2.x & 255u) == chk;
-            const u32 p0 = (s0.x >> 8) & 255u, p1 = (s1.x >> 8) & 255u, p2 = (s2.x >> 8) & 255u;
-            u8 *victim = (p0 <= p1 && p0 <= p2) ? b0 : (p1 < p2 ? b1 : b2);
-            const bool hit = m0 | m1 | m2;
-            slot_at = m0 ? b0 : m1 ? b1 : m2 ? b2 : victim;
-            const uint4 pick = m0 ? s0 : (m1 ? s1 : s2);
-            uint4 sl;
-            sl.x = hit ? pick.x : chk;
-            sl.y = hit ? pick.y : 0u;
-            sl.z = hit ? pick.z : 0u;
-            sl.w = hit ? pick.w : 0u;
-            *reinterpret_cast<uint4 *>(slots + 16 * pc) = sl;
-        }
-        q_ok = false;
+        uint4 sl = make_uint4(0, 0, 0, 0);
+        u32 grp;
+        actor = B::choose(c8v, sl, slot_at, grp);
+        if (actor) *reinterpret_cast<uint4 *>(slots + 16 * B::pc) = sl;
         __syncwarp();
     }
 };
