@@ -570,8 +570,13 @@ int run_decompress(zpaqgpu_ctx *ctx, DecompressJob &job, bool caller_owns_plain)
                             ctx->stats.paged = tp.paged ? 1 : 0;
                             ctx->stats.workspace_bytes_per_block = tp.stride;
                         }
-                        const int wpc = chain ? pick_warps_per_cta(ctx, m, tp.slots) : 4;
-                        ctx->stats.warps_per_cta = wpc;
+                        const bool tree2 = chain && ctx->decoder == 2 && tree2_supports(m);
+                        int wpc = chain ? pick_warps_per_cta(ctx, m, tp.slots) : 4;
+                        if (tree2) {
+                            const int per_sm = (tp.slots + ctx->sm_count - 1) / ctx->sm_count;
+                            wpc = std::max(1, std::min(tree2_max_pairs_per_cta(m), per_sm));
+                        }
+                        ctx->stats.warps_per_cta = tree2 ? 2 * wpc : wpc;
                         bool overflow = false;
                         for (int first = i; first < j && !overflow; first += tp.slots) {
                             const int cnt = std::min(tp.slots, j - first);
@@ -585,7 +590,7 @@ int run_decompress(zpaqgpu_ctx *ctx, DecompressJob &job, bool caller_owns_plain)
                             da.seg_count = static_cast<u32 *>(ctx->misc.p);
                             da.seg_cap = seg_cap, da.first_block = first, da.n_blocks = cnt;
                             da.order = reinterpret_cast<const u32 *>(static_cast<const u8 *>(ctx->desc.p) + o_dorder);
-                            da.flags = ctx->spec_probe ? 1 : 0;
+                            da.flags = (ctx->spec_probe ? 1 : 0) | (ctx->guess << 8) | (ctx->pull_how << 12);
                             CK(cudaEventRecord(ctx->ev[0], st));
                             if (store) {
                                 da.model = mod.dense;
@@ -595,7 +600,9 @@ int run_decompress(zpaqgpu_ctx *ctx, DecompressJob &job, bool caller_owns_plain)
                                 if ((rc = prepare_wave(ctx, mod, tp, cnt, da.model))) return rc;
                                 CK(cudaEventRecord(ctx->ev[1], st));
                                 if (chain) {
-                                    if (!launch_decode_chain(m, da, wpc, ctx->tree_decoder, st)) {
+                                    const bool ok = tree2 ? launch_decode_tree2(m, da, wpc, st)
+                                                          : launch_decode_chain(m, da, wpc, ctx->decoder != 0, st);
+                                    if (!ok) {
                                         ctx->err = "no chain kernel instantiation for this model";
                                         return ZPAQGPU_E_UNSUPPORTED;
                                     }
@@ -864,8 +871,11 @@ int zpaqgpu_init(zpaqgpu_ctx **out, int device) {
     if (cudaSetDevice(device) != cudaSuccess) return ZPAQGPU_E_NODEVICE;
     zpaqgpu_ctx *ctx = new zpaqgpu_ctx();
     ctx->device = device;
-    if (const char *v = std::getenv("ZPAQGPU_DECODER")) ctx->tree_decoder = std::strcmp(v, "serial") != 0;
+    if (const char *v = std::getenv("ZPAQGPU_DECODER"))
+        ctx->decoder = std::strcmp(v, "serial") == 0 ? 0 : (std::strcmp(v, "tree") == 0 ? 1 : 2);
     if (const char *v = std::getenv("ZPAQGPU_SPEC_PROBE")) ctx->spec_probe = std::atoi(v) != 0;
+    if (const char *v = std::getenv("ZPAQGPU_PULL")) ctx->pull_how = std::atoi(v) & 3;
+    if (const char *v = std::getenv("ZPAQGPU_GUESS")) ctx->guess = std::max(0, std::min(4, std::atoi(v)));
     if (const char *v = std::getenv("ZPAQGPU_ENC_FLAGS")) ctx->enc_l1_pull = std::atoi(v) != 0;
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->sm_count = prop.multiProcessorCount;
@@ -877,7 +887,7 @@ int zpaqgpu_init(zpaqgpu_ctx **out, int device) {
     ok = ok && cudaEventCreateWithFlags(&ctx->ev_main, cudaEventDisableTiming) == cudaSuccess;
     // constant tables: narrowed on the host, uploaded once
     const Tables &T = tables();
-    const size_t bytes = 32768 * 2 + 4096 * 2 + 512 + 1024 * 4 + 256 * 4 + 4096 * 2 + 32768 * 2;
+    const size_t bytes = 32768 * 2 + 4096 * 2 + 512 + 1024 * 4 + 256 * 4 + 4096 * 2 + 32768 * 2 + 32;
     std::vector<uint8_t> img(bytes);
     int16_t *st = reinterpret_cast<int16_t *>(img.data());
     uint16_t *sq = reinterpret_cast<uint16_t *>(img.data() + 65536);
@@ -897,6 +907,10 @@ int zpaqgpu_init(zpaqgpu_ctx **out, int device) {
         sqp[j] = uint16_t(T.squash[idx]);
     }
     for (int i = 0; i < 32768; ++i) stp[i] = int16_t(T.stretch[i < 1 ? 1 : i]);
+    uint32_t *lk = reinterpret_cast<uint32_t *>(stp + 32768);
+    for (int w = 0; w < 8; ++w) lk[w] = 0;
+    for (int s = 0; s < 256; ++s)
+        if (T.ns[s * 4 + 3] > T.ns[s * 4 + 2]) lk[s >> 5] |= 1u << (s & 31);
     ok = ok && cudaMalloc(&ctx->tables_mem, bytes) == cudaSuccess;
     ok = ok && cudaMemcpy(ctx->tables_mem, img.data(), bytes, cudaMemcpyHostToDevice) == cudaSuccess;
     if (!ok) {
@@ -912,6 +926,7 @@ int zpaqgpu_init(zpaqgpu_ctx **out, int device) {
     ctx->tables.dt2k = ctx->tables.dt + 1024;
     ctx->tables.squash_pad = reinterpret_cast<const u16 *>(ctx->tables.dt2k + 256);
     ctx->tables.stretch_pad = reinterpret_cast<const int16_t *>(ctx->tables.squash_pad + 4096);
+    ctx->tables.likely = reinterpret_cast<const u32 *>(ctx->tables.stretch_pad + 32768);
     *out = ctx;
     return ZPAQGPU_OK;
 }

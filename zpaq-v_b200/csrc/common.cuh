@@ -25,6 +25,8 @@ struct DevTables {
     const u8 *nex;           // 512 entries: nex[s*2+y] = next state (statetable.v ns[s*4+y])
     const i32 *dt;           // 1024 entries (CM)
     const i32 *dt2k;         // 256 entries (MATCH)
+    const u32 *likely;       // 8 words: bit s set when bit-history state s has seen more ones than zeros
+                             // (statetable.v n1 > n0); only steers prefetches, never a result
 };
 
 // Model as the kernels see it (pointers are device pointers).

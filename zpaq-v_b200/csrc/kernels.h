@@ -53,6 +53,11 @@ int encpipe_max_blocks_per_cta(const Model &m);
 bool launch_decode_chain(const Model &m, const DecodeArgs &A, int warps_per_cta, bool tree, cudaStream_t s);
 size_t chain_smem_bytes(const Model &m, int warps_per_cta);
 int chain_max_warps_per_cta(const Model &m);
+// Two-warp tree decoder (kernels_dectree.cu): ICM + up to four ISSEs, no MIX2.
+bool tree2_supports(const Model &m);
+bool launch_decode_tree2(const Model &m, const DecodeArgs &A, int pairs_per_cta, cudaStream_t s);
+size_t tree2_smem_bytes(const Model &m, int pairs_per_cta);
+int tree2_max_pairs_per_cta(const Model &m);
 
 // ---- auxiliary kernels (kernels_aux.cu) ----
 struct ShaJob {

@@ -637,7 +637,7 @@ __global__ void __launch_bounds__(256, 1) k_decode_chain(DecodeArgs A) {
     C.setup(smem + kSharedTables + size_t(wic) * warp_smem_bytes(NI, MIX2), A.model, ws,
             reinterpret_cast<const int16_t *>(smem), reinterpret_cast<const u16 *>(smem + 65536),
             smem + 65536 + 8192);
-    C.spec = A.flags != 0;
+    C.spec = (A.flags & 1) != 0;
     const DecBlock blk = A.blocks[bi];
     const u8 *arc = A.arc;
     u64 pos = blk.arc_pos;  // uniform across the warp
