@@ -152,3 +152,23 @@ def text_blocks(n_blocks, block_bytes, seed=SEED0):
 def text_stream(n, seed=SEED0, first=0):
     """numpy uint8 view of text_range, for bench.py (no per-block slicing copies)."""
     return np.frombuffer(text_range(first, n, seed), dtype=np.uint8)
+
+
+def mixed_stream(n_blocks, block_bytes, seed=SEED0 + 3):
+    """cfg 3 for the bench, generated in one go: block k is text if k%4 in {0,1} (consecutive slices of
+    the text stream of `seed`), uniform random bytes if k%4==2 (seed + k), structured binary if k%4==3
+    (seed + k).  Returns one uint8 array of n_blocks * block_bytes bytes."""
+    out = np.empty(n_blocks * block_bytes, dtype=np.uint8)
+    n_text = sum(1 for k in range(n_blocks) if k % 4 < 2)
+    txt = np.frombuffer(text_range(0, max(n_text, 1) * block_bytes, seed), dtype=np.uint8)
+    t = 0
+    for k in range(n_blocks):
+        dst = out[k * block_bytes:(k + 1) * block_bytes]
+        if k % 4 < 2:
+            dst[:] = txt[t * block_bytes:(t + 1) * block_bytes]
+            t += 1
+        elif k % 4 == 2:
+            dst[:] = np.frombuffer(random_bytes(block_bytes, seed + k), dtype=np.uint8)
+        else:
+            dst[:] = np.frombuffer(structured(block_bytes, seed + k), dtype=np.uint8)
+    return out

@@ -480,6 +480,7 @@ struct DecCandidate {
     u64 payload;     // offset of the first segment marker
     int group = -1;  // index into models, -1: header rejected
     u64 hint = 0;    // plaintext capacity to reserve
+    bool hinted = false;  // the capacity comes from the segment comment
     u64 out_off = 0;
     DecBlockOut res{};
 };
@@ -784,11 +785,35 @@ int decode_archive_dev(zpaqgpu_ctx *ctx, const uint8_t *arc, u64 len, std::vecto
             c.group = it->second;
             const u64 hint = comment_hint(arc, len, c.payload);
             c.hint = hint ? hint : 4 * (len - c.payload > (1u << 20) ? (1u << 20) : len - c.payload) + 65536;
+            c.hinted = hint != 0;
         } else {
             c.group = hrc == ZPAQGPU_E_UNSUPPORTED ? -2 : -1;
             c.hint = 0;
         }
         job.cand.push_back(c);
+    }
+    // The "<N> bytes" comment is untrusted input and a stored block may hold locators of its own: a
+    // slot is never larger than what the bytes up to the next candidate can plausibly decode to, and all
+    // slots together stay inside a share of the free memory.  An under-estimate only costs the sizing
+    // retry of run_decompress (the kernels report the true length).
+    {
+        size_t free_b = 0, total_b = 0;
+        CK(cudaMemGetInfo(&free_b, &total_b));
+        const u64 budget = std::max<u64>(u64(free_b + ctx->plain.cap) / 2, 1u << 20);
+        u64 sum = 0;
+        for (size_t i = 0; i < job.cand.size(); ++i) {
+            DecCandidate &c = job.cand[i];
+            if (c.group < 0) continue;
+            const u64 next = i + 1 < job.cand.size() ? job.cand[i + 1].start : len;
+            const u64 csz = next > c.payload ? next - c.payload : 0;
+            c.hint = std::min<u64>(c.hint, 4096 * csz + (1u << 20));
+            sum += c.hint;
+        }
+        if (sum > budget) {
+            const u64 share = std::max<u64>(budget / std::max<size_t>(1, job.cand.size()), 65536);
+            for (DecCandidate &c : job.cand)
+                if (c.group >= 0) c.hint = std::min<u64>(c.hint, share);
+        }
     }
     // 3. decode
     if (!job.cand.empty() && !job.models.empty()) {
@@ -859,6 +884,7 @@ const char *zpaqgpu_strerror(int code) {
 }
 
 int zpaqgpu_init(zpaqgpu_ctx **out, int device) {
+    return zg::guarded<int>(static_cast<zpaqgpu_ctx *>(nullptr), [&]() -> int {
     if (!out) return ZPAQGPU_E_ARG;
     *out = nullptr;
     int count = 0;
@@ -929,6 +955,7 @@ int zpaqgpu_init(zpaqgpu_ctx **out, int device) {
     ctx->tables.likely = reinterpret_cast<const u32 *>(ctx->tables.stretch_pad + 32768);
     *out = ctx;
     return ZPAQGPU_OK;
+    });
 }
 
 void zpaqgpu_destroy(zpaqgpu_ctx *ctx) {
@@ -977,10 +1004,12 @@ int zpaqgpu_set_stream(zpaqgpu_ctx *ctx, void *cuda_stream) {
 }
 
 int zpaqgpu_level_header(int level, uint8_t *out, int cap) {
+    return zg::guarded<int>(static_cast<zpaqgpu_ctx *>(nullptr), [&]() -> int {
     const std::vector<uint8_t> h = level_header(level);
     if (int(h.size()) > cap || !out) return ZPAQGPU_E_NOSPACE;
     std::memcpy(out, h.data(), h.size());
     return int(h.size());
+    });
 }
 
 int zpaqgpu_tables(int32_t *squash4096, int32_t *stretch32768, uint8_t *state1024) {
@@ -992,6 +1021,7 @@ int zpaqgpu_tables(int32_t *squash4096, int32_t *stretch32768, uint8_t *state102
 }
 
 int zpaqgpu_describe_model(const uint8_t *header, int header_len, zpaqgpu_model_info *out) {
+    return zg::guarded<int>(static_cast<zpaqgpu_ctx *>(nullptr), [&]() -> int {
     if (!out) return ZPAQGPU_E_ARG;
     Model m;
     const int rc = model_from_level_layout(header, header_len, m);
@@ -1005,6 +1035,7 @@ int zpaqgpu_describe_model(const uint8_t *header, int header_len, zpaqgpu_model_
     for (const CompDesc &c : m.comps)
         if (c.type == C_ICM || c.type == C_ISSE) out->hash_table_bytes += c.ht_len;
     return ZPAQGPU_OK;
+    });
 }
 
 int zpaqgpu_last_stats(const zpaqgpu_ctx *ctx, zpaqgpu_stats *out) {
@@ -1018,6 +1049,7 @@ int zpaqgpu_compress_blocks_header(zpaqgpu_ctx *ctx, const uint8_t *header, int 
                                    const uint64_t *in_off, int n_blocks, const char *const *names,
                                    const char *const *comments, uint8_t *out, uint64_t out_cap,
                                    uint64_t *out_off, uint64_t *out_need) {
+    return zg::guarded<int>(ctx, [&]() -> int {
     if (!ctx) return ZPAQGPU_E_ARG;
     Model m;
     const int rc = model_from_level_layout(header, header_len, m);
@@ -1026,19 +1058,23 @@ int zpaqgpu_compress_blocks_header(zpaqgpu_ctx *ctx, const uint8_t *header, int 
         return rc;
     }
     return compress_host(ctx, m, in, in_off, n_blocks, names, comments, out, out_cap, out_off, out_need);
+    });
 }
 
 int zpaqgpu_compress_blocks(zpaqgpu_ctx *ctx, int level, const uint8_t *in, const uint64_t *in_off, int n_blocks,
                             const char *const *names, const char *const *comments, uint8_t *out,
                             uint64_t out_cap, uint64_t *out_off, uint64_t *out_need) {
+    return zg::guarded<int>(ctx, [&]() -> int {
     const std::vector<uint8_t> h = level_header(level);
     return zpaqgpu_compress_blocks_header(ctx, h.data(), int(h.size()), in, in_off, n_blocks, names, comments,
                                           out, out_cap, out_off, out_need);
+    });
 }
 
 int zpaqgpu_compress_blocks_dev(zpaqgpu_ctx *ctx, int level, const void *d_in, const void *d_in_off,
                                 const uint64_t *h_in_off, int n_blocks, void *d_out, uint64_t out_cap,
                                 void *d_out_off, uint64_t *out_total) {
+    return zg::guarded<int>(ctx, [&]() -> int {
     (void)d_in_off;
     if (!ctx || n_blocks <= 0 || !h_in_off || !d_out || !d_out_off) return ZPAQGPU_E_ARG;
     CK(cudaSetDevice(ctx->device));
@@ -1065,11 +1101,13 @@ int zpaqgpu_compress_blocks_dev(zpaqgpu_ctx *ctx, int level, const void *d_in, c
     if ((rc = run_compress(ctx, job))) return rc;
     if (out_total) *out_total = job.total;
     return job.fits ? ZPAQGPU_OK : ZPAQGPU_E_NOSPACE;
+    });
 }
 
 // ---- locator scan ----
 int zpaqgpu_find_blocks(zpaqgpu_ctx *ctx, const uint8_t *arc, uint64_t len, uint64_t *starts, int cap,
                         int *n_found) {
+    return zg::guarded<int>(ctx, [&]() -> int {
     if (!ctx || (len && !arc) || cap < 0 || !n_found) return ZPAQGPU_E_ARG;
     *n_found = 0;
     if (len == 0) return ZPAQGPU_OK;
@@ -1095,11 +1133,13 @@ int zpaqgpu_find_blocks(zpaqgpu_ctx *ctx, const uint8_t *arc, uint64_t len, uint
     std::sort(tmp.begin(), tmp.end());
     if (count) std::memcpy(starts, tmp.data(), 8 * size_t(count));
     return ZPAQGPU_OK;
+    });
 }
 
 // ---- whole-archive decompression ----
 int zpaqgpu_decompress_archive(zpaqgpu_ctx *ctx, const uint8_t *arc, uint64_t len, uint8_t *out, uint64_t out_cap,
                                uint64_t *out_need, zpaqgpu_segment *segs, int segs_cap, int *n_segs) {
+    return zg::guarded<int>(ctx, [&]() -> int {
     if (!ctx || (len && !arc)) return ZPAQGPU_E_ARG;
     if (out_need) *out_need = 0;
     if (n_segs) *n_segs = 0;
@@ -1133,10 +1173,12 @@ int zpaqgpu_decompress_archive(zpaqgpu_ctx *ctx, const uint8_t *arc, uint64_t le
     CK(cudaStreamSynchronize(st));
     ctx->stats.d2h_ms = elapsed(ctx->ev[6], ctx->ev[7]);
     return status;
+    });
 }
 
 int zpaqgpu_decompress_blocks_dev(zpaqgpu_ctx *ctx, const void *d_arc, const uint64_t *h_arc_off, int n_blocks,
                                   void *d_out, const uint64_t *h_out_off, void *d_out_len, int *n_bad) {
+    return zg::guarded<int>(ctx, [&]() -> int {
     if (!ctx || n_blocks <= 0 || !d_arc || !h_arc_off || !d_out || !h_out_off) return ZPAQGPU_E_ARG;
     CK(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
@@ -1191,10 +1233,12 @@ int zpaqgpu_decompress_blocks_dev(zpaqgpu_ctx *ctx, const void *d_arc, const uin
     if (d_out_len) CK(cudaMemcpy(d_out_len, lens.data(), 8 * size_t(n_blocks), cudaMemcpyHostToDevice));
     if (n_bad) *n_bad = bad;
     return ZPAQGPU_OK;
+    });
 }
 
 // ---- streaming-shaped calls ----
 int zpaqgpu_block_begin_header(zpaqgpu_ctx *ctx, const uint8_t *header, int header_len) {
+    return zg::guarded<int>(ctx, [&]() -> int {
     if (!ctx) return ZPAQGPU_E_ARG;
     if (ctx->st_state != 2) return ZPAQGPU_E_STATE;  // compressor.v:80-82
     const int rc = model_from_level_layout(header, header_len, ctx->st_model);
@@ -1203,12 +1247,16 @@ int zpaqgpu_block_begin_header(zpaqgpu_ctx *ctx, const uint8_t *header, int head
     ctx->st_has_done = false;
     ctx->st_state = 0;
     return ZPAQGPU_OK;
+    });
 }
 int zpaqgpu_block_begin(zpaqgpu_ctx *ctx, int level) {
+    return zg::guarded<int>(ctx, [&]() -> int {
     const std::vector<uint8_t> h = level_header(level);
     return zpaqgpu_block_begin_header(ctx, h.data(), int(h.size()));
+    });
 }
 int zpaqgpu_segment_begin(zpaqgpu_ctx *ctx, const char *filename, const char *comment) {
+    return zg::guarded<int>(ctx, [&]() -> int {
     if (!ctx) return ZPAQGPU_E_ARG;
     if (ctx->st_state != 0) return ZPAQGPU_E_STATE;  // compressor.v:213-215
     PendingSeg s;
@@ -1216,14 +1264,17 @@ int zpaqgpu_segment_begin(zpaqgpu_ctx *ctx, const char *filename, const char *co
     ctx->st_segs.push_back(std::move(s));
     ctx->st_state = 1;
     return ZPAQGPU_OK;
+    });
 }
 int zpaqgpu_segment_write(zpaqgpu_ctx *ctx, const uint8_t *data, uint64_t len) {
+    return zg::guarded<int>(ctx, [&]() -> int {
     if (!ctx || (len && !data)) return ZPAQGPU_E_ARG;
     if (ctx->st_state != 1) return ZPAQGPU_E_STATE;  // compressor.v:260-262
     PendingSeg &s = ctx->st_segs.back();
     s.called = true;
     s.data.insert(s.data.end(), data, data + len);
     return ZPAQGPU_OK;
+    });
 }
 int zpaqgpu_segment_end(zpaqgpu_ctx *ctx) {
     if (!ctx) return ZPAQGPU_E_ARG;
@@ -1232,6 +1283,7 @@ int zpaqgpu_segment_end(zpaqgpu_ctx *ctx) {
     return ZPAQGPU_OK;
 }
 int64_t zpaqgpu_block_end(zpaqgpu_ctx *ctx, uint8_t *out, uint64_t cap, uint64_t *need) {
+    return zg::guarded<int64_t>(ctx, [&]() -> int64_t {
     if (!ctx) return ZPAQGPU_E_ARG;
     if (!ctx->st_has_done) {
         if (ctx->st_state != 0) return ZPAQGPU_E_STATE;  // compressor.v:403-405
@@ -1293,6 +1345,7 @@ int64_t zpaqgpu_block_end(zpaqgpu_ctx *ctx, uint8_t *out, uint64_t cap, uint64_t
     ctx->st_segs.clear();
     ctx->st_state = 2;
     return n;
+    });
 }
 
 }  // extern "C"

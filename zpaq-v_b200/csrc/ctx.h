@@ -1,6 +1,8 @@
 // ctx.h -- internals of libzpaqgpu shared by api.cu and jidac.cu: the context, grow-only device
 // buffers and the compression job that both the block API and the jidac front end submit.
 #pragma once
+#include <exception>
+#include <new>
 #include <string>
 #include <vector>
 
@@ -77,6 +79,23 @@ struct zpaqgpu_ctx {
     } while (0)
 
 namespace zg {
+
+// Nothing may leave the C ABI as a C++ exception: host allocation failures and the like become status codes.
+template <class R, class F>
+R guarded(zpaqgpu_ctx *ctx, F &&f) noexcept {
+    try {
+        return f();
+    } catch (const std::bad_alloc &) {
+        if (ctx) ctx->err = "host allocation failed";
+        return R(ZPAQGPU_E_NOMEM);
+    } catch (const std::exception &e) {
+        if (ctx) ctx->err = e.what();
+        return R(ZPAQGPU_E_CUDA);
+    } catch (...) {
+        if (ctx) ctx->err = "unknown exception";
+        return R(ZPAQGPU_E_CUDA);
+    }
+}
 
 struct CompressJob {
     const Model *model;

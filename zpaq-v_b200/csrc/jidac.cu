@@ -313,6 +313,12 @@ int jidac_front(zpaqgpu_ctx *ctx, const uint8_t *in, const uint64_t *in_off, int
     zpaqgpu_jidac_stats &S = ctx->jd_stats;
     S = zpaqgpu_jidac_stats{};
     S.n_files = n_files;
+    // -1: one fragment per file; 0..22 rolling hash; above: fixed size.  Beyond 40 the 64-bit fragment
+    // limits (64 << fragment, 8128 << fragment) would wrap.
+    if (fragment < -1 || fragment > 40) {
+        ctx->err = "fragment must be in -1..40";
+        return ZPAQGPU_E_ARG;
+    }
     if (n_files == 0) return ZPAQGPU_OK;
     cudaStream_t st = ctx->stream;
     const u64 base = in_off[0];
@@ -481,6 +487,7 @@ int zpaqgpu_jidac_last_stats(const zpaqgpu_ctx *ctx, zpaqgpu_jidac_stats *out) {
 
 int zpaqgpu_jidac_fragment(zpaqgpu_ctx *ctx, const uint8_t *in, const uint64_t *in_off, int n_files, int fragment,
                            int dedup, zpaqgpu_fragment *frags, int cap, int *n_frags, int *n_stored) {
+    return zg::guarded<int>(ctx, [&]() -> int {
     if (!ctx || n_files < 0 || (n_files > 0 && !in_off) || !n_frags) return ZPAQGPU_E_ARG;
     CK(cudaSetDevice(ctx->device));
     Front R;
@@ -498,11 +505,13 @@ int zpaqgpu_jidac_fragment(zpaqgpu_ctx *ctx, const uint8_t *in, const uint64_t *
         std::memcpy(f.sha1, R.digests.data() + 20 * size_t(i), 20);
     }
     return ZPAQGPU_OK;
+    });
 }
 
 int zpaqgpu_jidac_extract(zpaqgpu_ctx *ctx, const uint8_t *arc, uint64_t len, uint8_t *out, uint64_t out_cap,
                           uint64_t *out_need, zpaqgpu_jidac_file *files, int files_cap, int *n_files, char *names,
                           uint64_t names_cap, uint64_t *names_need) {
+    return zg::guarded<int>(ctx, [&]() -> int {
     if (!ctx || (len && !arc)) return ZPAQGPU_E_ARG;
     if (out_need) *out_need = 0;
     if (n_files) *n_files = 0;
@@ -557,6 +566,11 @@ int zpaqgpu_jidac_extract(zpaqgpu_ctx *ctx, const uint8_t *arc, uint64_t len, ui
     // d blocks by their first fragment id; fragments from the h tables
     struct Frag { u64 src; u32 len; u8 sha1[20]; bool known = false; };
     std::vector<Frag> frags(1);  // ids are 1-based
+    // an id can never exceed the number of table entries in the archive: a 10-digit block number from
+    // a damaged or crafted archive must not size an allocation
+    u64 h_entries = 0;
+    for (const JSeg &j : js)
+        if (j.kind == 'h' && j.s->seg.out_len >= 4) h_entries += (j.s->seg.out_len - 4) / 24;
     std::vector<std::pair<u32, const DecodedSeg *>> dsegs;
     for (const JSeg &j : js)
         if (j.kind == 'd') dsegs.emplace_back(j.num, j.s);
@@ -580,6 +594,10 @@ int zpaqgpu_jidac_extract(zpaqgpu_ctx *ctx, const uint8_t *arc, uint64_t len, ui
                 u64 off = 0;
                 u32 id = j.num;
                 for (u64 q = 4; q + 24 <= n; q += 24, ++id) {
+                    if (id == 0 || u64(id) > h_entries) {
+                        ctx->err = "fragment id outside the tables of the archive";
+                        return ZPAQGPU_E_FORMAT;
+                    }
                     if (frags.size() <= id) frags.resize(size_t(id) + 1);
                     Frag &f = frags[id];
                     std::memcpy(f.sha1, p + q, 20);
@@ -701,11 +719,13 @@ int zpaqgpu_jidac_extract(zpaqgpu_ctx *ctx, const uint8_t *arc, uint64_t len, ui
     ctx->jd_stats.n_files = int(live.size()), ctx->jd_stats.n_fragments = int(sj.size());
     ctx->jd_stats.input_bytes = len, ctx->jd_stats.stored_bytes = total, ctx->jd_stats.archive_bytes = len;
     return ZPAQGPU_OK;
+    });
 }
 
 int zpaqgpu_jidac_add(zpaqgpu_ctx *ctx, const zpaqgpu_jidac_opts *opts, const char *const *names, const uint8_t *in,
                       const uint64_t *in_off, int n_files, uint8_t *out, uint64_t out_cap, uint64_t *out_len,
                       uint64_t *out_need) {
+    return zg::guarded<int>(ctx, [&]() -> int {
     if (!ctx || !opts || n_files < 0 || (n_files > 0 && (!in_off || !names))) return ZPAQGPU_E_ARG;
     if (opts->level < 0 || opts->level > 5) return ZPAQGPU_E_ARG;
     CK(cudaSetDevice(ctx->device));
@@ -858,6 +878,7 @@ int zpaqgpu_jidac_add(zpaqgpu_ctx *ctx, const zpaqgpu_jidac_opts *opts, const ch
     CK(cudaStreamSynchronize(st));
     ctx->jd_stats.d2h_ms = t_d2h.ms();
     return ZPAQGPU_OK;
+    });
 }
 
 }  // extern "C"
