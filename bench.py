@@ -2,7 +2,7 @@
 """bench.py -- headline benchmark of the B200 ZPAQ block codec.
 
 Metric (BASELINE.json): compress & decompress input MB/s per -mN at 1/2/4/8 B200 vs host CPU.
-Workload at N=1 (BASELINE.json configs[1]): -m2 (ICM + 2 x ISSE), 1 GiB of synthetic text in
+Workload of `value` (BASELINE.json configs[1]): -m2 (ICM + 2 x ISSE), 1 GiB of synthetic text in
 1024 independent 1 MiB blocks.  With N GPUs every rank gets its own 1 GiB (weak scaling): blocks
 are independent, so ranks share nothing on the data path; torch.distributed is only used for the
 barrier and the max-over-ranks of the timed region.
@@ -11,6 +11,13 @@ One step = compress every block, then decompress every block (one pass of the ho
 ways).  value = input bytes / (t_compress + t_decompress), inputs resident in HBM.  e2e = the same
 through the host-buffer C-ABI calls (zpaqgpu_compress_blocks / zpaqgpu_decompress_archive) with the
 host<->device copies inside the timed region.
+
+After the headline the same line gets a `per_level` block: one pass each of the other BASELINE.json
+configurations on the same GPU(s) -- -m1 and -m4 at 1024 x 1 MiB text, cfg 3 (-m3, 8 GiB mixed text /
+random / structured in 1 MiB blocks, the 8192 blocks split over the ranks: strong scaling), cfg 4 (-m5,
+1024 x 4 MiB text, decompression is the quoted figure), cfg 5 (jidac add of a 10 000-file tree, rank 0)
+-- each with kernel times from CUDA events, the issue-roofline fraction, table mode, waves and a
+byte-for-byte comparison of at least 8 blocks with the CPU oracle outside the timed region.
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--level L] [--blocks B] [--block-kib S]
   python bench.py --impl reference ...   # the reference algorithm on the host cores (CPU oracle)
@@ -32,6 +39,7 @@ METRIC = "compress & decompress input MB/s per -mN at 1/2/4/8 B200 vs host CPU"
 # integer ops per input byte for m1..m5 (counted from the reference source)
 W_OPS = {1: 1010, 2: 1430, 3: 2300, 4: 3000, 5: 3870}
 N_HT = {1: 2, 2: 3, 3: 5, 4: 6, 5: 8}
+N_SM, LANES = 148, 128
 
 
 def parse():
@@ -45,6 +53,12 @@ def parse():
     ap.add_argument("--block-kib", type=int, default=1024)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--e2e-steps", type=int, default=5, help="cap of the end-to-end timed steps (stated in the line)")
+    ap.add_argument("--per-level", default="1,3,4,5,jidac", help="extra configurations after the headline")
+    ap.add_argument("--no-per-level", action="store_true")
+    ap.add_argument("--cfg3-blocks", type=int, default=8192, help="cfg 3: blocks of 1 MiB over ALL ranks")
+    ap.add_argument("--cfg4-blocks", type=int, default=1024, help="cfg 4: blocks of 4 MiB per rank")
+    ap.add_argument("--jidac-files", type=int, default=10000)
     return ap.parse_args()
 
 
@@ -52,9 +66,9 @@ def peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
             p = json.load(f)
-        return float(p["hbm_gbs"]), float(p.get("sm_max_mhz", 1965.0)), "measured"
+        return float(p["hbm_gbs"]), float(p.get("sm_max_mhz", 1965.0)), "measured (MEASURED_PEAKS.json)"
     except Exception:
-        return 6650.0, 1965.0, "fallback"
+        return 6650.0, 1965.0, "fallback (B200_PROFILING.md)"
 
 
 class ClockSampler:
@@ -114,31 +128,38 @@ class ClockSampler:
         return out
 
 
-def oracle_run(level, data, n_blocks, block_bytes, threads):
-    """Compress then decompress n_blocks with the CPU oracle on `threads` host threads.
-    Returns (t_compress, t_decompress, archive_bytes)."""
+def oracle_blocks(level, src, offs, threads):
+    """The CPU oracle over blocks src[offs[k]:offs[k+1]] on `threads` host threads: compress, then
+    decompress.  Returns (t_compress, t_decompress, archive array, archive offsets)."""
     import numpy as np
     import oracle_binding as ob
     L = ob.lib()
-    off = (C.c_uint64 * (n_blocks + 1))(*[i * block_bytes for i in range(n_blocks + 1)])
-    cap = n_blocks * (block_bytes + block_bytes // 4 + 4096)
+    n = len(offs) - 1
+    total = int(offs[-1] - offs[0])
+    off = (C.c_uint64 * (n + 1))(*[int(x) for x in offs])
+    cap = total + total // 2 + 4096 * n
     out = np.empty(cap, dtype=np.uint8)
-    out_off = (C.c_uint64 * (n_blocks + 1))()
+    out_off = (C.c_uint64 * (n + 1))()
     need = C.c_uint64(0)
-    src = np.ascontiguousarray(data[:n_blocks * block_bytes])
+    src = np.ascontiguousarray(src)
     t0 = time.perf_counter()
-    rc = L.zo_compress_blocks_mt(level, src.ctypes.data, off, n_blocks, out.ctypes.data, cap, out_off,
-                                 C.byref(need), threads)
+    rc = L.zo_compress_blocks_mt(level, src.ctypes.data, off, n, out.ctypes.data, cap, out_off, C.byref(need), threads)
     t1 = time.perf_counter()
-    assert rc == 0
-    back = np.empty(n_blocks * block_bytes + 16, dtype=np.uint8)
-    back_off = (C.c_uint64 * (n_blocks + 1))()
-    rc = L.zo_decompress_blocks_mt(out.ctypes.data, out_off, n_blocks, back.ctypes.data, len(back), back_off,
+    assert rc == 0, "oracle compress failed (%d)" % rc
+    back = np.empty(total + 16, dtype=np.uint8)
+    back_off = (C.c_uint64 * (n + 1))()
+    rc = L.zo_decompress_blocks_mt(out.ctypes.data, out_off, n, back.ctypes.data, len(back), back_off,
                                    C.byref(need), threads)
     t2 = time.perf_counter()
-    assert rc == 0 and need.value == n_blocks * block_bytes
-    assert bytes(back[:need.value]) == bytes(src), "oracle round trip failed"
-    return t1 - t0, t2 - t1, int(out_off[n_blocks]), out, out_off
+    assert rc == 0 and need.value == total
+    assert bytes(back[:total]) == bytes(src[int(offs[0]):int(offs[-1])]), "oracle round trip failed"
+    return t1 - t0, t2 - t1, out, [int(out_off[k]) for k in range(n + 1)]
+
+
+def oracle_run(level, data, n_blocks, block_bytes, threads):
+    a, b, out, out_off = oracle_blocks(level, data[:n_blocks * block_bytes],
+                                       [i * block_bytes for i in range(n_blocks + 1)], threads)
+    return a, b, out_off[-1], out, out_off
 
 
 def cpu_sample_blocks(level, cores, block_bytes):
@@ -190,7 +211,103 @@ def config_dict(args):
                         % (args.level, args.blocks, args.block_kib),
             "level": args.level, "blocks_per_gpu": args.blocks, "block_bytes": args.block_kib * 1024,
             "l2": "inputs (%d MiB per GPU) exceed the 126 MB L2, no flush needed" % (args.blocks * args.block_kib // 1024),
-            "parallelism": "one ZPAQ block per warp; disjoint block ranges per GPU, no collective"}
+            "parallelism": "one ZPAQ block per warp group; disjoint block ranges per GPU, no collective"}
+
+
+def load_traffic():
+    """DRAM bytes per launch of the codec kernels from the committed ncu pass on the bench configuration
+    (profiles/r02_traffic.json, written by tools/ncu_traffic.py from profiles/r02_traffic_launches.csv)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r02_traffic.json")) as f:
+            return json.load(f)
+    except Exception:
+        return None
+
+
+class DeviceCodec:
+    """compress_blocks_dev / decompress_blocks_dev over equal-sized blocks resident in HBM."""
+
+    def __init__(self, z, zb, torch, dev, stream_ptr):
+        self.z, self.zb, self.torch, self.dev = z, zb, torch, dev
+        self.L = zb.lib()
+        self.ctx = z.Context(dev.index)
+        self.ctx.set_stream(stream_ptr)
+
+    def close(self):
+        self.ctx.close()
+
+    def alloc(self, nb, bb, slack=4):
+        t = self.torch
+        total = nb * bb
+        self.nb, self.bb, self.total = nb, bb, total
+        self.cap = total + total // slack + 4096 * nb
+        self.d_arc = t.empty(self.cap, dtype=t.uint8, device=self.dev)
+        self.d_arc_off = t.zeros(nb + 1, dtype=t.int64, device=self.dev)
+        self.d_plain = t.empty(total, dtype=t.uint8, device=self.dev)
+        self.d_plain_len = t.zeros(nb, dtype=t.int64, device=self.dev)
+        self.in_off = (C.c_uint64 * (nb + 1))(*[i * bb for i in range(nb + 1)])
+
+    def step(self, level, d_in):
+        """Returns (t_compress_s, t_decompress_s, archive_bytes, stats_c, stats_d); times from CUDA events
+        on the stream the kernels run on."""
+        import numpy as np
+        t, ctx, L, nb = self.torch, self.ctx, self.L, self.nb
+        e = [t.cuda.Event(enable_timing=True) for _ in range(4)]
+        tot = C.c_uint64(0)
+        e[0].record()
+        ctx._check(L.zpaqgpu_compress_blocks_dev(ctx._h, level, d_in.data_ptr(), None, self.in_off, nb,
+                                                 self.d_arc.data_ptr(), self.cap, self.d_arc_off.data_ptr(),
+                                                 C.byref(tot)))
+        e[1].record()
+        st_c = ctx.stats()
+        arc_off_h = self.d_arc_off.cpu().numpy().astype(np.uint64)
+        arc_off_c = (C.c_uint64 * (nb + 1))(*arc_off_h.tolist())
+        bad = C.c_int(0)
+        e[2].record()
+        ctx._check(L.zpaqgpu_decompress_blocks_dev(ctx._h, self.d_arc.data_ptr(), arc_off_c, nb, self.d_plain.data_ptr(),
+                                                   self.in_off, self.d_plain_len.data_ptr(), C.byref(bad)))
+        e[3].record()
+        t.cuda.synchronize()
+        st_d = ctx.stats()
+        if bad.value:
+            raise SystemExit("decompression reported %d bad blocks" % bad.value)
+        return e[0].elapsed_time(e[1]) / 1e3, e[2].elapsed_time(e[3]) / 1e3, int(tot.value), st_c, st_d
+
+    def block_bytes_of(self, b):
+        off = self.d_arc_off[b:b + 2].cpu().numpy()
+        return bytes(self.d_arc[int(off[0]):int(off[1])].cpu().numpy())
+
+
+def parity_blocks(codec, level, host_np, idx, cores):
+    """Blocks idx of the last compress step, byte for byte against the CPU oracle (comment "<n> bytes",
+    empty name: what compress_blocks_dev writes)."""
+    import numpy as np
+    import oracle_binding as ob
+    bb = codec.bb
+    if len(idx) <= 2:
+        return all(codec.block_bytes_of(b) == ob.compress_block(level, host_np[b * bb:(b + 1) * bb].tobytes(), "",
+                                                                  "%d bytes" % bb) for b in idx)
+    sample = np.concatenate([host_np[b * bb:(b + 1) * bb] for b in idx])
+    _, _, out, out_off = oracle_blocks(level, sample, [k * bb for k in range(len(idx) + 1)], min(cores, len(idx)))
+    # zo_compress_blocks_mt writes the same framing (empty name, "<n> bytes")
+    return all(codec.block_bytes_of(b) == bytes(out[out_off[k]:out_off[k + 1]]) for k, b in enumerate(idx))
+
+
+def issue_frac(level, input_bytes, seconds, f_clk_hz):
+    return input_bytes / seconds * W_OPS[level] / (N_SM * LANES * f_clk_hz)
+
+
+def hbm_block(level, ratio, ws_bytes_per_block, paged, bb, input_bytes, seconds, hbm_peak):
+    """algorithmic HBM bytes per input byte = 1 (read) + ratio (write) + table bytes cleared per
+    block / block size; the upper bound adds every probe as a miss: 2 probes x n_ht x 64 B x 2 (read +
+    write-back).  No speculative reads are counted."""
+    alg = 1.0 + ratio + ws_bytes_per_block / bb
+    upper = alg + 2 * N_HT[level] * 128
+    ach = input_bytes * alg / seconds / 1e9
+    return {"algorithmic_bytes_per_input_byte": round(alg, 3), "all_probes_miss_bytes_per_input_byte": round(upper, 3),
+            "table_bytes_cleared_per_block": int(ws_bytes_per_block), "tables": "paged" if paged else "dense",
+            "achieved": round(ach, 3), "peak": hbm_peak, "unit": "GB/s", "frac": round(ach / hbm_peak, 6),
+            "frac_if_all_probes_miss": round(input_bytes * upper / seconds / 1e9 / hbm_peak, 6)}
 
 
 def main():
@@ -214,9 +331,8 @@ def main():
     if world > 1:
         import torch.distributed as dist_
         dist = dist_
-        # rank 0 prints ONE JSON line on stdout: NCCL's version banner (printed by the library when the
-        # first communicator comes up) is kept off fd 1
-        os.environ["NCCL_DEBUG"] = "WARN"
+        # rank 0 prints ONE JSON line on stdout: whatever NCCL prints while the communicator comes up is
+        # kept off fd 1 (NCCL_DEBUG itself is left as the caller set it)
         sys.stdout.flush()
         saved, null = os.dup(1), os.open(os.devnull, os.O_WRONLY)
         os.dup2(null, 1)
@@ -232,58 +348,33 @@ def main():
     level, nb, bb = args.level, args.blocks, args.block_kib * 1024
     total = nb * bb
     dev = torch.device("cuda", local)
+    cores = os.cpu_count() or 1
+    hbm_peak, sm_max, peak_kind = peaks()
     # every rank codes its own stretch of the text stream
     host_np = datagen.text_stream(total, first=rank * total)
     host_in = torch.from_numpy(host_np.copy()).pin_memory()
     d_in = host_in.to(dev, non_blocking=False)
-    cap = total + total // 4 + 4096 * nb
-    d_arc = torch.empty(cap, dtype=torch.uint8, device=dev)
-    d_arc_off = torch.zeros(nb + 1, dtype=torch.int64, device=dev)
-    d_plain = torch.empty(total, dtype=torch.uint8, device=dev)
-    d_plain_len = torch.zeros(nb, dtype=torch.int64, device=dev)
-    in_off = (C.c_uint64 * (nb + 1))(*[i * bb for i in range(nb + 1)])
 
-    ctx = z.Context(local)
-    ctx.set_stream(torch.cuda.current_stream().cuda_stream)
-    L = zb.lib()
+    codec = DeviceCodec(z, zb, torch, dev, torch.cuda.current_stream().cuda_stream)
+    codec.alloc(nb, bb)
+    ctx, L = codec.ctx, codec.L
     launches = {"n": 0}
     kern_ms = {"enc": 0.0, "dec": 0.0, "enc_n": 0, "dec_n": 0}
-
-    def step_device(timed):
-        """compress + decompress with inputs resident in HBM; returns (t_c, t_d) in seconds"""
-        e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
-        tot = C.c_uint64(0)
-        e[0].record()
-        ctx._check(L.zpaqgpu_compress_blocks_dev(ctx._h, level, d_in.data_ptr(), None, in_off, nb, d_arc.data_ptr(),
-                                                 cap, d_arc_off.data_ptr(), C.byref(tot)))
-        e[1].record()
-        st_c = ctx.stats()
-        arc_off_h = d_arc_off.cpu().numpy().astype(np.uint64)
-        arc_off_c = (C.c_uint64 * (nb + 1))(*arc_off_h.tolist())
-        bad = C.c_int(0)
-        e1b = torch.cuda.Event(enable_timing=True)
-        e1b.record()
-        ctx._check(L.zpaqgpu_decompress_blocks_dev(ctx._h, d_arc.data_ptr(), arc_off_c, nb, d_plain.data_ptr(), in_off,
-                                                   d_plain_len.data_ptr(), C.byref(bad)))
-        e[2].record()
-        torch.cuda.synchronize()
-        st_d = ctx.stats()
-        if bad.value:
-            raise SystemExit("decompression reported %d bad blocks" % bad.value)
-        if timed:
-            launches["n"] += st_c["launches"] + st_d["launches"]
-            kern_ms["enc"] += st_c["codec_ms"]; kern_ms["enc_n"] += st_c["codec_launches"]
-            kern_ms["dec"] += st_d["codec_ms"]; kern_ms["dec_n"] += st_d["codec_launches"]
-        return e[0].elapsed_time(e[1]) / 1e3, e1b.elapsed_time(e[2]) / 1e3, int(tot.value), st_c, st_d
 
     def barrier():
         if dist is not None:
             dist.barrier()
         torch.cuda.synchronize()
 
+    def allmax(vals):
+        t = torch.tensor(vals, dtype=torch.float64, device=dev)
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return [float(x) for x in t.cpu()]
+
     for _ in range(args.warmup):
-        step_device(False)
-    if not torch.equal(d_plain, d_in):
+        codec.step(level, d_in)
+    if not torch.equal(codec.d_plain, d_in):
         raise SystemExit("round trip mismatch on the device path")
     clocks = ClockSampler(local if os.environ.get("CUDA_VISIBLE_DEVICES") is None else
                           int(os.environ["CUDA_VISIBLE_DEVICES"].split(",")[local]))
@@ -294,33 +385,28 @@ def main():
     arc_total = 0
     st_c = st_d = None
     for _ in range(args.steps):
-        a, b, arc_total, st_c, st_d = step_device(True)
+        a, b, arc_total, st_c, st_d = codec.step(level, d_in)
         tc += a
         td += b
+        launches["n"] += st_c["launches"] + st_d["launches"]
+        kern_ms["enc"] += st_c["codec_ms"]; kern_ms["enc_n"] += st_c["codec_launches"]
+        kern_ms["dec"] += st_d["codec_ms"]; kern_ms["dec_n"] += st_d["codec_launches"]
     barrier()
     clk = clocks.stop() if rank == 0 else {}
-    t_all = torch.tensor([tc + td, tc, td], dtype=torch.float64, device=dev)
-    if dist is not None:
-        dist.all_reduce(t_all, op=dist.ReduceOp.MAX)
-    t_sum, t_c, t_d = [float(x) for x in t_all.cpu()]
+    t_sum, t_c, t_d = allmax([tc + td, tc, td])
     bytes_all = total * world * args.steps
     value = bytes_all / t_sum / 1e6
 
-    # parity sample against the oracle (outside the timed region): first blocks byte-identical
+    # parity against the oracle (outside the timed region): 8 blocks spread over the batch, byte-identical
     parity = None
+    parity_idx = sorted(set(int(x) for x in np.linspace(0, nb - 1, 8)))
     if rank == 0:
-        import oracle_binding as ob
-        arc_off_h = d_arc_off.cpu().numpy()
-        ok = True
-        for b in (0, nb - 1):
-            want = ob.compress_block(level, host_np[b * bb:(b + 1) * bb].tobytes(), "", "%d bytes" % bb)
-            got = bytes(d_arc[int(arc_off_h[b]):int(arc_off_h[b + 1])].cpu().numpy())
-            ok = ok and got == want
-        parity = bool(ok)
+        parity = bool(parity_blocks(codec, level, host_np, parity_idx, cores))
 
     # ---- end to end through the host-buffer C ABI ----
     e2e = None
     if not args.no_e2e:
+        cap = codec.cap
         host_arc = torch.empty(cap, dtype=torch.uint8).pin_memory()
         host_out = torch.empty(total, dtype=torch.uint8).pin_memory()
         out_off = (C.c_uint64 * (nb + 1))()
@@ -331,7 +417,7 @@ def main():
 
         def step_host():
             t0 = time.perf_counter()
-            ctx._check(L.zpaqgpu_compress_blocks(ctx._h, level, host_in.data_ptr(), in_off, nb, None, comments,
+            ctx._check(L.zpaqgpu_compress_blocks(ctx._h, level, host_in.data_ptr(), codec.in_off, nb, None, comments,
                                                  host_arc.data_ptr(), cap, out_off, C.byref(need)))
             t1 = time.perf_counter()
             arc_len = int(out_off[nb])
@@ -341,7 +427,7 @@ def main():
             t2 = time.perf_counter()
             return t1 - t0, t2 - t1, arc_len
 
-        e_steps = max(1, min(args.steps, 2))
+        e_steps = max(1, min(args.steps, args.e2e_steps))
         step_host()
         if not torch.equal(host_out, host_in):
             raise SystemExit("round trip mismatch on the host path")
@@ -353,70 +439,67 @@ def main():
             hc += a
             hd += b
         barrier()
-        t_h = torch.tensor([hc + hd], dtype=torch.float64, device=dev)
-        if dist is not None:
-            dist.all_reduce(t_h, op=dist.ReduceOp.MAX)
-        e2e = {"value": round(total * world * e_steps / float(t_h.item()) / 1e6, 3), "unit": "MB/s",
+        t_h = allmax([hc + hd])[0]
+        e2e = {"value": round(total * world * e_steps / t_h / 1e6, 3), "unit": "MB/s",
                "h2d_bytes_per_step": int(total + arc_len), "d2h_bytes_per_step": int(arc_len + total),
                "compress_mb_s": round(total * e_steps / hc / 1e6, 3),
-               "decompress_mb_s": round(total * e_steps / hd / 1e6, 3), "steps": e_steps}
+               "decompress_mb_s": round(total * e_steps / hd / 1e6, 3), "steps": e_steps,
+               "steps_note": "host-timed (perf_counter around the C-ABI calls, copies inside); capped at --e2e-steps "
+                             "so that the per-level passes fit the run"}
+        del host_arc, host_out
 
-    if rank != 0:
-        if dist is not None:
-            dist.destroy_process_group()
-        return 0
-
-    # ---- roofline of the dominant kernel ----
-    # The decode kernel takes the larger share of the step; the encoder is reported beside it.
-    hbm_peak, sm_max, peak_kind = peaks()
+    # ---- roofline of the dominant kernel (the per-SM integer issue roofline) ----
     ratio = arc_total / total
-    n_ht = N_HT.get(level, 3)
-    # algorithmic bytes per input byte the codec kernel asks of the memory system:
-    # plaintext (1) + coded bytes (ratio) + per nibble and hash-table component one 64-byte probe line
-    # read and one 16-byte slot write-back (2 nibbles per byte).  The tree decoder (-m1..-m3) requests
-    # the four possible lines of the next nibble two bits early: four line reads per probe instead of one.
-    tree_dec = level <= 3 and os.environ.get("ZPAQGPU_DECODER", "tree") != "serial"
-    spec = 4 if (tree_dec and os.environ.get("ZPAQGPU_SPEC_PROBE", "1") != "0") else 1
-    alg_enc = 1.0 + ratio + 2 * n_ht * (64 + 16)
-    alg_dec = 1.0 + ratio + 2 * n_ht * (64 * spec + 16)
-    enc_ms = kern_ms["enc"] / max(1, kern_ms["enc_n"])
-    dec_ms = kern_ms["dec"] / max(1, kern_ms["dec_n"])
-    launch_bytes = total / max(1, st_d["waves"])
-    f_clk = (clk.get("sm_mhz") or sm_max) * 1e6
-    issue_peak = 148 * 128 * f_clk
-    traffic = {"encode": None, "decode": None}
-    try:
-        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-            tj = json.load(f)
-        if level == 2:
-            traffic = {k: round(tj[k]["dram_bytes_per_input_byte"] * launch_bytes) for k in ("encode", "decode")}
-    except Exception:
-        pass
+    f_clk = (clk.get("sm_mhz") or sm_max) * 1e6 if rank == 0 else sm_max * 1e6
+    roofline = None
+    if rank == 0:
+        enc_ms = kern_ms["enc"] / max(1, kern_ms["enc_n"])
+        dec_ms = kern_ms["dec"] / max(1, kern_ms["dec_n"])
+        launch_bytes = total / max(1, st_d["waves"])
+        issue_peak = N_SM * LANES * f_clk
+        tj = load_traffic()
 
-    def roof(ms, name, key, alg):
-        ach = launch_bytes * alg / (ms / 1e3) / 1e9
-        return {"kernel": name, "achieved": round(ach, 2), "frac": round(ach / hbm_peak, 5), "kernel_ms": round(ms, 3),
-                "traffic": traffic[key], "algorithmic_bytes_per_input_byte": round(alg, 2),
-                "issue_frac": round(launch_bytes / (ms / 1e3) * W_OPS.get(level, 0) / issue_peak, 5)}
+        def traffic_of(key):
+            if not tj or key not in tj:
+                return None
+            t = tj[key]
+            same = t.get("level") == level and t.get("blocks") == nb and t.get("block_bytes") == bb
+            return int(t["dram_bytes_per_launch"]) if same else None
 
-    n_isse = N_HT.get(level, 3) - 1
-    mix = "true" if level >= 4 else "false"
-    dec_r = roof(dec_ms, "k_decode_chain<%d,%s,%s>" % (n_isse, mix, "true" if tree_dec else "false"), "decode", alg_dec)
-    enc_r = roof(enc_ms, "k_encode_pipe3<%d,%s>" % (n_isse, mix), "encode", alg_enc)
-    roofline = {
-        "bound": "hbm", "kernel": dec_r["kernel"], "achieved": dec_r["achieved"], "peak": hbm_peak, "unit": "GB/s",
-        "frac": dec_r["frac"], "peak_source": peak_kind, "traffic": dec_r["traffic"],
-        "algorithmic_bytes_per_input_byte": dec_r["algorithmic_bytes_per_input_byte"], "units_per_launch": int(launch_bytes),
-        "kernel_ms": dec_r["kernel_ms"], "encode": enc_r,
-        "note": "bit-serial integer chain: the binding limit is the dependent-instruction latency of one warp per "
-                "block, not HBM; issue_roofline = W(L) ops/byte x bytes/s / (148 SM x 128 lanes x f_clk)",
-        "issue_roofline": {"ops_per_input_byte": W_OPS.get(level), "decode_frac": dec_r["issue_frac"],
-                           "encode_frac": enc_r["issue_frac"], "peak_ops_per_s": issue_peak, "sm_mhz": f_clk / 1e6},
-    }
+        n_isse = N_HT.get(level, 3) - 1
+        mix = "true" if level >= 4 else "false"
+        dec_name = os.environ.get("ZPAQGPU_DECODER", "tree")
+        tree_dec = level <= 3 and dec_name != "serial"
+        if tree_dec and dec_name == "tree2":
+            dec_kernel = "k_decode_tree2<%d>" % n_isse
+        else:
+            dec_kernel = "k_decode_chain<%d,%s,%s>" % (n_isse, mix, "true" if tree_dec else "false")
+
+        def kern(ms, name, key, st):
+            ach = launch_bytes / (ms / 1e3) * W_OPS[level]
+            return {"kernel": name, "kernel_ms": round(ms, 3), "achieved": round(ach / 1e12, 5),
+                    "frac": round(ach / issue_peak, 5), "traffic": traffic_of(key),
+                    "hbm": hbm_block(level, ratio, st["workspace_bytes_per_block"], st["paged"], bb, launch_bytes,
+                                     ms / 1e3, hbm_peak)}
+
+        dec_r = kern(dec_ms, dec_kernel, "decode", st_d)
+        enc_r = kern(enc_ms, "k_encode_pipe3<%d,%s>" % (n_isse, mix), "encode", st_c)
+        dom, other = (dec_r, enc_r) if dec_ms >= enc_ms else (enc_r, dec_r)
+        roofline = {
+            "bound": "issue", "kernel": dom["kernel"], "achieved": dom["achieved"], "peak": round(issue_peak / 1e12, 4),
+            "unit": "Tops/s", "frac": dom["frac"], "traffic": dom["traffic"], "kernel_ms": dom["kernel_ms"],
+            "ops_per_input_byte": W_OPS[level], "units_per_launch": int(launch_bytes),
+            "peak_source": "148 SM x 128 INT32 lanes x f_clk (SURVEY 8(d)); f_clk = median SM clock sampled during the "
+                           "timed region (%.0f MHz)" % (f_clk / 1e6),
+            "formula": "achieved = W(L) ops/B x units_per_launch / kernel time (CUDA events around the launch); "
+                       "frac = achieved / peak",
+            "traffic_source": "ncu dram__bytes_read.sum + dram__bytes_write.sum per launch on this configuration "
+                              "(profiles/r02_traffic_launches.csv)" if dom["traffic"] else None,
+            "hbm": dict(dom["hbm"], peak_source=peak_kind), "other_kernel": other,
+        }
 
     cpu = None
-    if not args.no_cpu_baseline:
-        cores = os.cpu_count() or 1
+    if rank == 0 and not args.no_cpu_baseline:
         n_s = min(nb, cpu_sample_blocks(level, cores, bb))
         a, b, _, _, _ = oracle_run(level, host_np, n_s, bb, cores)
         cpu = {"value": round(n_s * bb / (a + b) / 1e6, 3), "unit": "MB/s", "cores": cores, "kind": "port",
@@ -424,20 +507,172 @@ def main():
                          "V reference) on %d threads" % (n_s, nb, args.block_kib, cores),
                "compress_mb_s": round(n_s * bb / a / 1e6, 3), "decompress_mb_s": round(n_s * bb / b / 1e6, 3)}
 
+    # ---- the other BASELINE.json configurations ----
+    codec.close()
+    del codec, d_in, host_in
+    torch.cuda.empty_cache()
+    per_level = None
+    if not args.no_per_level:
+        per_level = run_per_level(args, dict(z=z, zb=zb, torch=torch, np=np, datagen=datagen, dev=dev, rank=rank,
+                                             world=world, barrier=barrier, allmax=allmax, f_clk=f_clk, cores=cores,
+                                             hbm_peak=hbm_peak, text=host_np))
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return 0
+
     line = {
         "metric": METRIC, "value": round(value, 3), "unit": "MB/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": round(t_sum / args.steps * 1e3, 3), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
         "config": config_dict(args),
         "compress_mb_s": round(bytes_all / t_c / 1e6, 3), "decompress_mb_s": round(bytes_all / t_d / 1e6, 3),
-        "ratio": round(ratio, 4), "byte_identical_to_oracle": parity,
+        "ratio": round(ratio, 4), "byte_identical_to_oracle": parity, "parity_blocks": parity_idx,
         "e2e": e2e, "gpu_launches": launches["n"], "clocks": clk, "roofline": roofline, "cpu_baseline": cpu,
-        "stats": {"compress": st_c, "decompress": st_d},
+        "per_level": per_level, "stats": {"compress": st_c, "decompress": st_d},
     }
     print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()
     return 0
+
+
+def run_per_level(args, E):
+    """One pass of every other BASELINE.json configuration.  Kernel times come from CUDA events around the
+    launches (zpaqgpu_last_stats); the per-call times from events around the device-pointer calls."""
+    torch, np, datagen, dev = E["torch"], E["np"], E["datagen"], E["dev"]
+    rank, world = E["rank"], E["world"]
+    want = [x.strip() for x in args.per_level.split(",") if x.strip()]
+    out = {}
+
+    def one(key, level, data_np, nb, bb, scaling, what, warm_blocks=148):
+        """data_np: this rank's input (nb * bb bytes, host)."""
+        codec = DeviceCodec(E["z"], E["zb"], torch, dev, torch.cuda.current_stream().cuda_stream)
+        try:
+            total = nb * bb
+            d_in = torch.from_numpy(data_np).to(dev)
+            # a small pass first: module load, first-touch of the constant tables, buffer growth
+            wb = min(nb, warm_blocks)
+            codec.alloc(wb, bb, slack=2)
+            codec.step(level, d_in[:wb * bb])
+            codec.alloc(nb, bb, slack=2 if level == 3 else 4)
+            E["barrier"]()
+            t_c, t_d, arc, st_c, st_d = codec.step(level, d_in)
+            E["barrier"]()
+            if not torch.equal(codec.d_plain, d_in):
+                raise SystemExit("per-level %s: round trip mismatch" % key)
+            idx = sorted(set(int(x) for x in np.linspace(0, nb - 1, 8)))
+            ok = bool(parity_blocks(codec, level, data_np, idx, E["cores"])) if rank == 0 else None
+            m_c, m_d, k_c, k_d = E["allmax"]([t_c, t_d, st_c["codec_ms"] / 1e3, st_d["codec_ms"] / 1e3])
+            all_bytes = total * world
+            return {
+                "what": what, "level": level, "blocks_per_gpu": nb, "block_bytes": bb, "scaling": scaling,
+                "input_bytes_all_gpus": all_bytes,
+                "compress_mb_s": round(all_bytes / m_c / 1e6, 2), "decompress_mb_s": round(all_bytes / m_d / 1e6, 2),
+                "compress_kernel_mb_s": round(all_bytes / k_c / 1e6, 2),
+                "decompress_kernel_mb_s": round(all_bytes / k_d / 1e6, 2),
+                "compress_kernel_ms": round(st_c["codec_ms"], 2), "decompress_kernel_ms": round(st_d["codec_ms"], 2),
+                "issue_frac": {"compress": round(issue_frac(level, total, k_c, E["f_clk"]), 5),
+                               "decompress": round(issue_frac(level, total, k_d, E["f_clk"]), 5)},
+                "hbm": {"compress": hbm_block(level, arc / total, st_c["workspace_bytes_per_block"], st_c["paged"], bb,
+                                              total, k_c, E["hbm_peak"]),
+                        "decompress": hbm_block(level, arc / total, st_d["workspace_bytes_per_block"], st_d["paged"],
+                                                bb, total, k_d, E["hbm_peak"])},
+                "ratio": round(arc / total, 4),
+                "tables": ["paged" if st_c["paged"] else "dense", "paged" if st_d["paged"] else "dense"],
+                "waves": [st_c["waves"], st_d["waves"]], "retries": [st_c["retries"], st_d["retries"]],
+                "pool_mb_used": [round(st_c["pool_bytes_used"] / 1e6, 1), round(st_d["pool_bytes_used"] / 1e6, 1)],
+                "warps_per_cta": [st_c["warps_per_cta"], st_d["warps_per_cta"]],
+                "byte_identical_to_oracle": ok, "parity_blocks": idx, "round_trip_exact": True,
+                "timing": "one pass after a %d-block warm-up pass; CUDA events" % wb,
+            }
+        finally:
+            codec.close()
+            del codec
+            torch.cuda.empty_cache()
+
+    text = E["text"]  # this rank's 1 GiB (or --blocks x --block-kib) of the text stream
+    mib = 1 << 20
+    n_text_mib = len(text) // mib
+    for key in want:
+        try:
+            if key in ("1", "4") and n_text_mib >= 1:
+                out["m" + key] = one("m" + key, int(key), text[:n_text_mib * mib], n_text_mib, mib, "weak",
+                                     "-m%s, %d x 1 MiB text per GPU" % (key, n_text_mib))
+            elif key == "3":
+                # cfg 3: the 8192 blocks of 1 MiB are split over the ranks in contiguous ranges (strong
+                # scaling).  1024 distinct mixed blocks are generated and repeated to fill a rank's range.
+                per = max(1, args.cfg3_blocks // world)
+                distinct = min(per, 1024)
+                base = datagen.mixed_stream(distinct, mib, datagen.SEED0 + 3 + 1000 * rank)
+                reps = (per + distinct - 1) // distinct
+                data = np.tile(base, reps)[:per * mib] if reps > 1 else base
+                out["m3"] = one("m3", 3, data, per, mib, "strong",
+                                "cfg 3: -m3, %d x 1 MiB mixed text/random/structured over %d GPU(s) (%d distinct "
+                                "blocks per GPU, repeated)" % (per * world, world, distinct))
+                del data, base
+            elif key == "5":
+                # cfg 4: -m5, 4 MiB blocks of text; the rank's text stream repeated to fill the blocks
+                bb = 4 * mib
+                nbk = max(1, args.cfg4_blocks)
+                have = (len(text) // bb) * bb
+                if have == 0:
+                    continue
+                reps = (nbk * bb + have - 1) // have
+                data = np.tile(text[:have], reps)[:nbk * bb] if reps > 1 else text[:nbk * bb]
+                out["m5"] = one("m5", 5, np.ascontiguousarray(data), nbk, bb, "weak",
+                                "cfg 4: -m5, %d x 4 MiB text per GPU (%d distinct blocks, repeated); decompression "
+                                "is the quoted figure" % (nbk, have // bb), warm_blocks=16)
+                del data
+            elif key == "jidac" and rank == 0:
+                out["jidac_add"] = run_jidac(args, E)
+        except SystemExit:
+            raise
+        except Exception as ex:  # a configuration that cannot run is reported, never silently dropped
+            out["m" + key if key != "jidac" else "jidac_add"] = {"error": "%s: %s" % (type(ex).__name__, ex)}
+            torch.cuda.empty_cache()
+    E["barrier"]()
+    return out
+
+
+def run_jidac(args, E):
+    """cfg 5: jidac add of the synthetic tree through zpaqgpu_jidac_add with HOST buffers (rank 0's GPU)."""
+    np, datagen = E["np"], E["datagen"]
+    import oracle_binding as ob
+    z, zb = E["z"], E["zb"]
+    DATE = 20260101120000
+    names, files = datagen.file_tree(args.jidac_files)
+    total = sum(map(len, files))
+    kw = dict(level=1, fragment=6, dedup=True, block_bytes=1 << 20)
+    ctx = z.Context(E["dev"].index)
+    try:
+        ctx.jidac_add(names[:4], files[:4], DATE, **kw)
+        src = np.frombuffer(b"".join(files), dtype=np.uint8)
+        off = np.zeros(len(files) + 1, dtype=np.uint64)
+        off[1:] = np.cumsum([len(f) for f in files])
+        arr = (C.c_char_p * len(names))(*[n.encode() for n in names])
+        opts = zb.JidacOpts(DATE, kw["level"], kw["fragment"], 1, 0, kw["block_bytes"])
+        outb = np.empty(total + total // 4 + 4096 * (len(files) + 4), dtype=np.uint8)
+        ln, need = C.c_uint64(0), C.c_uint64(0)
+        t0 = time.perf_counter()
+        rc = zb.lib().zpaqgpu_jidac_add(ctx._h, C.byref(opts), arr, src.ctypes.data, off.ctypes.data, len(files),
+                                        outb.ctypes.data, outb.nbytes, C.byref(ln), C.byref(need))
+        t1 = time.perf_counter()
+        ctx._check(rc)
+        st = ctx.jidac_stats()
+        k = min(100, len(files))
+        want = ob.jidac_add(names[:k], files[:k], DATE, **kw)
+        got = ctx.jidac_add(names[:k], files[:k], DATE, **kw)
+        return {"what": "cfg 5: jidac add, %d files (1 KiB..1 MiB, 30 %% duplicates), fragment 6, dedup, -m1, 1 MiB d "
+                        "blocks, host buffers in and out, one GPU" % len(files),
+                "input_bytes": total, "add_mb_s": round(total / (t1 - t0) / 1e6, 2), "archive_bytes": int(ln.value),
+                "stages_ms": {s: round(st[s], 2) for s in ("h2d_ms", "fragment_ms", "sha1_ms", "dedup_ms", "gather_ms",
+                                                           "codec_ms", "pack_ms", "d2h_ms")},
+                "n_fragments": st["n_fragments"], "n_stored": st["n_stored"], "n_dblocks": st["n_dblocks"],
+                "stored_bytes": st["stored_bytes"], "launches": st["launches"],
+                "byte_identical_to_oracle_on_subtree": got == want, "subtree_files": k}
+    finally:
+        ctx.close()
 
 
 if __name__ == "__main__":

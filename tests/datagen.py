@@ -172,3 +172,23 @@ def mixed_stream(n_blocks, block_bytes, seed=SEED0 + 3):
         else:
             dst[:] = np.frombuffer(structured(block_bytes, seed + k), dtype=np.uint8)
     return out
+
+
+def file_tree(n_files, seed=SEED0 + 5):
+    """cfg 5: n_files files, sizes log-uniform 1 KiB..1 MiB, 30 % exact duplicates of an earlier file,
+    text/binary 70/30.  Returns (names, [bytes...]) in sorted path order."""
+    r = _xorshift_stream(seed, n_files * 3)
+    u = (r[:n_files] >> np.uint64(11)).astype(np.float64) / float(1 << 53)
+    sizes = np.exp(np.log(1024) + u * (np.log(1 << 20) - np.log(1024))).astype(np.int64)
+    files = []
+    pool = text(256 << 20, SEED0 + 55)
+    for k in range(n_files):
+        if k > 10 and int(r[n_files + k] % np.uint64(10)) < 3:
+            files.append(files[int(r[2 * n_files + k] % np.uint64(k))])
+        elif int(r[n_files + k] % np.uint64(100)) < 70:
+            at = int(r[2 * n_files + k] % np.uint64((256 << 20) - (1 << 20)))
+            files.append(pool[at:at + int(sizes[k])])
+        else:
+            files.append(structured(int(sizes[k]), SEED0 + k))
+    names = ["dir%02d/file%05d" % (k % 37, k) for k in range(n_files)]
+    return names, files

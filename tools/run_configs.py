@@ -36,20 +36,7 @@ def make(cfg, args):
         whole = datagen.text(args.blocks * bb, datagen.SEED0 + 4)
         return 5, [whole[i * bb:(i + 1) * bb] for i in range(args.blocks)]
     if cfg == 5:
-        # 10k files, sizes log-uniform 1 KiB..1 MiB, 30 % exact duplicates, text/binary 70/30
-        r = datagen._xorshift_stream(datagen.SEED0 + 5, args.files * 3)
-        u = (r[:args.files] >> np.uint64(11)).astype(np.float64) / float(1 << 53)
-        sizes = np.exp(np.log(1024) + u * (np.log(1 << 20) - np.log(1024))).astype(np.int64)
-        files = []
-        pool = datagen.text(256 << 20, datagen.SEED0 + 55)
-        for k in range(args.files):
-            if k > 10 and int(r[args.files + k] % np.uint64(10)) < 3:
-                files.append(files[int(r[2 * args.files + k] % np.uint64(k))])
-            elif int(r[args.files + k] % np.uint64(100)) < 70:
-                at = int(r[2 * args.files + k] % np.uint64((256 << 20) - (1 << 20)))
-                files.append(pool[at:at + int(sizes[k])])
-            else:
-                files.append(datagen.structured(int(sizes[k]), datagen.SEED0 + k))
+        files = datagen.file_tree(args.files)[1]
         return 1, files
     raise SystemExit("cfg must be 2..5")
 
