@@ -9,9 +9,11 @@
  * Rules of the boundary: plain pointers and sizes only; the caller owns every host buffer; the
  * library owns device memory and pinned staging; errors are negative status codes, never aborts;
  * there is NO CPU fallback -- without a usable CUDA device every compute call returns
- * ZPAQGPU_E_NODEVICE.  A ctx is bound to one device and is single-threaded; one process per GPU
- * (or one ctx per GPU) is the multi-GPU model, no collective is involved because ZPAQ blocks are
- * independent (compressor.v:84-187 re-initialises all model state in start_block).
+ * ZPAQGPU_E_NODEVICE.  A ctx is bound to one device and is single-threaded.  Several GPUs of one
+ * box: either one process (or one ctx) per GPU, or ONE zpaqgpu_multi handle that owns a ctx, a host
+ * thread and a stream per device and splits every call into contiguous block ranges (section "several
+ * devices" below).  No collective is involved because ZPAQ blocks are independent (compressor.v:84-187
+ * re-initialises all model state in start_block).
  */
 #ifndef ZPAQGPU_H
 #define ZPAQGPU_H
@@ -162,6 +164,20 @@ int zpaqgpu_segment_end(zpaqgpu_ctx *ctx);
  * or ZPAQGPU_E_NOSPACE with *need set (call again with a larger buffer; the block is kept). */
 int64_t zpaqgpu_block_end(zpaqgpu_ctx *ctx, uint8_t *out, uint64_t cap, uint64_t *need);
 
+/* Many blocks one after the other -- the shape of cmd/main.v:288-317, one start_block..end_block per file.
+ * A block coded on its own runs ONE chain on a 148-SM GPU; queued blocks are coded together, a chain per
+ * block in one launch, and delivered in queue order, so the bytes and their order equal what per-block
+ * zpaqgpu_block_end calls give.  The shim's Compressor.end_block() calls zpaqgpu_block_end_queue and, when
+ * it returns 1 (queue limits reached: default 1024 blocks or 1 GiB of input, zpaqgpu_stream_batch), or
+ * before the output is closed (cmd/main.v:320), zpaqgpu_flush and writes the bytes to its Writer. */
+int zpaqgpu_stream_batch(zpaqgpu_ctx *ctx, int max_blocks, uint64_t max_bytes); /* 0 = default */
+/* Compressor.end_block() (compressor.v:402), deferred: 0 queued, 1 queued and the queue is full. */
+int zpaqgpu_block_end_queue(zpaqgpu_ctx *ctx);
+int zpaqgpu_queued(const zpaqgpu_ctx *ctx, int *n_blocks, uint64_t *in_bytes);
+/* Codes every queued block; returns the byte count written to out (0 when nothing is queued), or
+ * ZPAQGPU_E_NOSPACE with *need set (the coded bytes are kept: call again with a larger buffer). */
+int64_t zpaqgpu_flush(zpaqgpu_ctx *ctx, uint8_t *out, uint64_t cap, uint64_t *need);
+
 /* ---- jidac front end: fragmentation, fragment hashing, dedup, journaling archive ------------ */
 /* Stands in for JidacArchive.create_archive (jidac.v:181-296) and widens it by what the task's
  * north star asks of `jidac add`: content-defined fragmentation with a rolling hash and SHA-1
@@ -254,6 +270,40 @@ typedef struct {
     int32_t reserved;
 } zpaqgpu_stats;
 int zpaqgpu_last_stats(const zpaqgpu_ctx *ctx, zpaqgpu_stats *out);
+
+/* ---- several devices of one box behind one handle ---------------------- */
+/* One ctx + host thread + stream per device.  A call is split into contiguous ranges balanced by input
+ * bytes ("disjoint block ranges to each GPU", no collective), every device stages its range, then every
+ * device copies its result to its final place in the caller's buffer: the output is byte for byte what the
+ * single-device call writes, in block order.  devices == NULL or n_devices <= 0: all visible devices. */
+typedef struct zpaqgpu_multi zpaqgpu_multi;
+int zpaqgpu_multi_init(zpaqgpu_multi **out, const int *devices, int n_devices);
+void zpaqgpu_multi_destroy(zpaqgpu_multi *m);
+int zpaqgpu_multi_device_count(const zpaqgpu_multi *m);
+/* the k-th device's context, borrowed (for the zpaqgpu_set_* tuning calls) */
+zpaqgpu_ctx *zpaqgpu_multi_ctx(zpaqgpu_multi *m, int k);
+const char *zpaqgpu_multi_last_error(const zpaqgpu_multi *m);
+/* zpaqgpu_compress_blocks over all devices: same arguments, same bytes. */
+int zpaqgpu_multi_compress_blocks(zpaqgpu_multi *m, int level, const uint8_t *in, const uint64_t *in_off,
+                                  int n_blocks, const char *const *names, const char *const *comments,
+                                  uint8_t *out, uint64_t out_cap, uint64_t *out_off, uint64_t *out_need);
+/* zpaqgpu_decompress_archive over all devices: the archive is cut at the first locator at or after
+ * len*g/G; when a range does not end cleanly (a block runs across a cut: an archive stored inside an
+ * archive; or a damaged block, where the reference's walk stops) one device repeats the whole archive, so
+ * the result always equals the single-device call's. */
+int zpaqgpu_multi_decompress_archive(zpaqgpu_multi *m, const uint8_t *arc, uint64_t len, uint8_t *out,
+                                     uint64_t out_cap, uint64_t *out_need, zpaqgpu_segment *segs,
+                                     int segs_cap, int *n_segs);
+typedef struct {
+    int32_t device;          /* CUDA device index                                                */
+    int32_t first_unit;      /* first block of the device's range in the last call                */
+    int32_t n_units;         /* blocks in the range                                               */
+    int32_t fallback_single; /* 1: the last decompress call was repeated on one device            */
+    float stage_ms;          /* host time of phase 1 (upload + kernels) on this device            */
+    float fetch_ms;          /* host time of phase 2 (copy back)                                  */
+    zpaqgpu_stats stats;     /* the device's own counters                                         */
+} zpaqgpu_multi_stats;
+int zpaqgpu_multi_last_stats(const zpaqgpu_multi *m, int k, zpaqgpu_multi_stats *out);
 
 #if defined(__GNUC__)
 #pragma GCC visibility pop

@@ -7,9 +7,11 @@ its own tests hold no golden compressed bytes.  These vectors are therefore ORAC
 has and against the independent probe vectors of BASELINE.md section 4).  On a machine with V, the
 same inputs can be pushed through zpaq.Compressor to confirm them:
 
-    v run tests/golden/confirm_with_v.v
+    tools/confirm_with_v.sh /path/to/zpaq-v     # see INTEGRATION.md; needs `v` on PATH
 
-Run:  python tests/golden/make_golden.py
+Run:  python tests/golden/make_golden.py                       regenerate the json files from the oracle
+      python tests/golden/make_golden.py --write-inputs DIR    the nine inputs as files (for tools/ref_golden.v)
+      python tests/golden/make_golden.py --compare REF.txt     output of tools/ref_golden.v against the json files
 """
 import hashlib
 import json
@@ -89,5 +91,54 @@ def main():
     print("wrote", len(jd["archives"]), "jidac vectors")
 
 
+def write_inputs(dst):
+    os.makedirs(dst, exist_ok=True)
+    for name, data in inputs().items():
+        with open(os.path.join(dst, name), "wb") as f:
+            f.write(data)
+    print("wrote", len(inputs()), "inputs to", dst)
+
+
+def compare(ref_txt):
+    """Lines of tools/ref_golden.v (the V reference) against blocks.json / jidac.json (the oracle)."""
+    with open(os.path.join(HERE, "blocks.json")) as f:
+        want = {(b["level"], b["input"]): (b["len"], b["sha1"]) for b in json.load(f)["blocks"]}
+    with open(os.path.join(HERE, "jidac.json")) as f:
+        tiny = json.load(f)["tiny_reference_hex"]
+    seen, bad = set(), []
+    for line in open(ref_txt):
+        parts = line.split()
+        if not parts:
+            continue
+        if parts[0] == "block":
+            key = (int(parts[1]), parts[2])
+            seen.add(key)
+            if key not in want:
+                bad.append("unexpected %r" % (key,))
+            elif want[key] != (int(parts[3]), parts[4]):
+                bad.append("level %d input %s: reference %s bytes sha1 %s, oracle %d bytes sha1 %s"
+                           % (key[0], key[1], parts[3], parts[4], want[key][0], want[key][1]))
+        elif parts[0] == "jidac_tiny":
+            seen.add("jidac")
+            if parts[1] != tiny:
+                bad.append("jidac tiny archive differs: reference %s..., oracle %s..." % (parts[1][:64], tiny[:64]))
+    for key in want:
+        if key not in seen:
+            bad.append("missing from the reference output: %r" % (key,))
+    if "jidac" not in seen:
+        bad.append("missing from the reference output: jidac_tiny")
+    if bad:
+        print("\n".join(bad))
+        print("PARITY WITH THE V REFERENCE: %d of %d vectors differ" % (len(bad), len(want) + 1))
+        sys.exit(1)
+    print("PARITY WITH THE V REFERENCE: all %d block vectors and the journaling archive are byte-identical"
+          % len(want))
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) == 3 and sys.argv[1] == "--write-inputs":
+        write_inputs(sys.argv[2])
+    elif len(sys.argv) == 3 and sys.argv[1] == "--compare":
+        compare(sys.argv[2])
+    else:
+        main()

@@ -93,7 +93,7 @@ def test_ctypes_structs_match_the_header(tmp_path):
     from zpaq_v_b200 import binding as zb
     structs = {"zpaqgpu_model_info": zb.ModelInfo, "zpaqgpu_segment": zb.Segment, "zpaqgpu_stats": zb.Stats,
                "zpaqgpu_jidac_opts": zb.JidacOpts, "zpaqgpu_fragment": zb.Fragment, "zpaqgpu_jidac_file": zb.JidacFile,
-               "zpaqgpu_jidac_stats": zb.JidacStats}
+               "zpaqgpu_jidac_stats": zb.JidacStats, "zpaqgpu_multi_stats": zb.MultiStats}
     lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "zpaqgpu.h"', 'int main(void) {']
     for cname, cls in structs.items():
         lines.append('printf("%s %%zu", sizeof(%s));' % (cname, cname))

@@ -82,3 +82,63 @@ def test_jidac_add_two_ranks_with_the_gpu_coder(gpu_ctx):
     one = sharding.jidac_add_sharded(_Rank(1, 0, {}), frag, comp, names, fl, DATE, level=1, fragment=2,
                                      block_bytes=16384)
     assert one == single == ob.jidac_add(names, fl, DATE, level=1, fragment=2, dedup=True, block_bytes=16384)
+
+
+# ---- several devices behind one C handle (zpaqgpu_multi, csrc/multi.cu) -------------------------------------
+def _devices(n):
+    """n device indices: distinct GPUs when the box has them, else the same GPU n times (the split, the
+    host threads and the two-phase landing are the same code either way)."""
+    import torch
+    have = torch.cuda.device_count()
+    return [k % have for k in range(n)]
+
+
+@pytest.mark.parametrize("world", [1, 2, 3])
+def test_multi_compress_equals_single_and_oracle(gpu_ctx, world):
+    import zpaq_v_b200 as z
+    m = z.Multi(_devices(world))
+    try:
+        assert m.device_count() == world
+        blocks = [datagen.mixed_block(k, 2000 + 3000 * (k % 5)) for k in range(11)] + [b""]
+        names = ["f%d" % k for k in range(len(blocks))]
+        comments = ["%d bytes" % len(b) for b in blocks]
+        got = m.compress_blocks(2, blocks, names=names, comments=comments)
+        assert got == [ob.compress_block(2, b, n, c) for b, n, c in zip(blocks, names, comments)]
+        assert got == gpu_ctx.compress_blocks(2, blocks, names=names, comments=comments)
+        st = m.stats()
+        assert sum(s["n_units"] for s in st) == len(blocks)
+        assert [s["first_unit"] for s in st] == sorted(s["first_unit"] for s in st)
+        if world > 1:
+            assert sum(1 for s in st if s["n_units"] > 0) > 1
+        # fewer blocks than devices, and none at all
+        assert m.compress_blocks(1, blocks[:1]) == [ob.compress_block(1, blocks[0], "", "")]
+        assert m.compress_blocks(1, []) == []
+        arc = b"".join(got)
+        plain, segs, status = m.decompress_archive(arc)
+        want_plain, want_segs, want_status = gpu_ctx.decompress_archive(arc)
+        assert (plain, segs, status) == (want_plain, want_segs, want_status)
+        assert plain == b"".join(blocks) and status == 0 and all(s["sha1_ok"] == 1 for s in segs)
+        assert [s["block_index"] for s in segs] == list(range(len(blocks)))
+    finally:
+        m.close()
+
+
+def test_multi_decompress_falls_back_when_a_block_spans_the_cut(gpu_ctx):
+    """An archive stored inside an archive: the locators of the inner blocks lie inside the outer block, so a
+    cut placed at one of them splits a block.  A damaged block in the middle stops the reference's walk.
+    Either way one device repeats the whole archive and the result equals the single-device call's."""
+    import zpaq_v_b200 as z
+    m = z.Multi(_devices(2))
+    try:
+        inner = b"".join(ob.compress_block(1, datagen.text(3000, 60 + k), "in%d" % k, "") for k in range(6))
+        outer = ob.compress_block(0, inner, "nested.zpaq", "") + ob.compress_block(2, b"after", "t", "")
+        got = m.decompress_archive(outer)
+        assert got == gpu_ctx.decompress_archive(outer) and got[0] == inner + b"after"
+        assert m.stats()[0]["fallback_single"] == 1
+        blocks = [ob.compress_block(2, datagen.text(4000, 70 + k), "b%d" % k, "") for k in range(6)]
+        bad = bytearray(b"".join(blocks))
+        bad[len(blocks[0]) + 16] = 9            # second block: level byte not 1/2, find_block fails there
+        got = m.decompress_archive(bytes(bad))
+        assert got == gpu_ctx.decompress_archive(bytes(bad)) and got[0] == datagen.text(4000, 70)
+    finally:
+        m.close()

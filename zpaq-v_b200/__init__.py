@@ -7,10 +7,10 @@ jidac.py   host mirror of the reference's JidacArchive (+ a reader)
 vshim/     the V-side binding a maintainer of the reference would add (not compilable here)
 """
 from . import binding
-from .binding import Context, ZpaqGpuError, describe_model, level_header, tables
+from .binding import Context, Multi, ZpaqGpuError, describe_model, level_header, tables
 from .codec import Compressor, Decompresser, FileReader, FileWriter
 from .jidac import JidacArchive
 from . import jidac
 
-__all__ = ["binding", "Context", "ZpaqGpuError", "level_header", "tables", "describe_model", "Compressor", "Decompresser",
+__all__ = ["binding", "Context", "Multi", "ZpaqGpuError", "level_header", "tables", "describe_model", "Compressor", "Decompresser",
            "FileReader", "FileWriter", "JidacArchive", "jidac"]

@@ -22,6 +22,10 @@ EXPORTS = [
     "zpaqgpu_block_begin", "zpaqgpu_block_begin_header", "zpaqgpu_segment_begin", "zpaqgpu_segment_write",
     "zpaqgpu_segment_end", "zpaqgpu_block_end", "zpaqgpu_last_stats", "zpaqgpu_describe_model",
     "zpaqgpu_jidac_fragment", "zpaqgpu_jidac_add", "zpaqgpu_jidac_extract", "zpaqgpu_jidac_last_stats",
+    "zpaqgpu_stream_batch", "zpaqgpu_block_end_queue", "zpaqgpu_queued", "zpaqgpu_flush",
+    "zpaqgpu_multi_init", "zpaqgpu_multi_destroy", "zpaqgpu_multi_device_count", "zpaqgpu_multi_ctx",
+    "zpaqgpu_multi_last_error", "zpaqgpu_multi_compress_blocks", "zpaqgpu_multi_decompress_archive",
+    "zpaqgpu_multi_last_stats",
 ]
 
 
@@ -47,6 +51,11 @@ class Stats(C.Structure):
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+class MultiStats(C.Structure):
+    _fields_ = [("device", C.c_int32), ("first_unit", C.c_int32), ("n_units", C.c_int32),
+                ("fallback_single", C.c_int32), ("stage_ms", C.c_float), ("fetch_ms", C.c_float), ("stats", Stats)]
 
 
 class JidacOpts(C.Structure):
@@ -127,6 +136,22 @@ def lib():
     L.zpaqgpu_jidac_last_stats.argtypes = [vp, C.POINTER(JidacStats)]
     L.zpaqgpu_jidac_extract.argtypes = [vp, vp, C.c_uint64, vp, C.c_uint64, u64p, vp, C.c_int, i32p, vp, C.c_uint64,
                                         u64p]
+    L.zpaqgpu_stream_batch.argtypes = [vp, C.c_int, C.c_uint64]
+    L.zpaqgpu_block_end_queue.argtypes = [vp]
+    L.zpaqgpu_queued.argtypes = [vp, i32p, u64p]
+    L.zpaqgpu_flush.argtypes = [vp, vp, C.c_uint64, u64p]
+    L.zpaqgpu_flush.restype = C.c_int64
+    L.zpaqgpu_multi_init.argtypes = [C.POINTER(vp), vp, C.c_int]
+    L.zpaqgpu_multi_destroy.argtypes = [vp]
+    L.zpaqgpu_multi_destroy.restype = None
+    L.zpaqgpu_multi_device_count.argtypes = [vp]
+    L.zpaqgpu_multi_ctx.argtypes = [vp, C.c_int]
+    L.zpaqgpu_multi_ctx.restype = vp
+    L.zpaqgpu_multi_last_error.argtypes = [vp]
+    L.zpaqgpu_multi_last_error.restype = C.c_char_p
+    L.zpaqgpu_multi_compress_blocks.argtypes = [vp, C.c_int, vp, vp, C.c_int, vp, vp, vp, C.c_uint64, vp, u64p]
+    L.zpaqgpu_multi_decompress_archive.argtypes = [vp, vp, C.c_uint64, vp, C.c_uint64, u64p, vp, C.c_int, i32p]
+    L.zpaqgpu_multi_last_stats.argtypes = [vp, C.c_int, C.POINTER(MultiStats)]
     _lib = L
     return L
 
@@ -381,6 +406,30 @@ class Context:
     def segment_end(self):
         return lib().zpaqgpu_segment_end(self._h)
 
+    def block_end_queue(self):
+        """Compressor.end_block(), deferred: 0 queued, 1 queued and the queue is full, < 0 error."""
+        return lib().zpaqgpu_block_end_queue(self._h)
+
+    def stream_batch(self, max_blocks=0, max_bytes=0):
+        self._check(lib().zpaqgpu_stream_batch(self._h, max_blocks, max_bytes))
+
+    def queued(self):
+        n, b = C.c_int(0), C.c_uint64(0)
+        self._check(lib().zpaqgpu_queued(self._h, C.byref(n), C.byref(b)))
+        return n.value, b.value
+
+    def flush(self):
+        """Codes every queued block in one batch; their bytes in queue order."""
+        need = C.c_uint64(0)
+        n = lib().zpaqgpu_flush(self._h, None, 0, C.byref(need))
+        if n == E_NOSPACE:
+            buf = C.create_string_buffer(max(need.value, 1))
+            n = lib().zpaqgpu_flush(self._h, buf, need.value, C.byref(need))
+            if n >= 0:
+                return buf.raw[:n]
+        self._check(n)
+        return b""
+
     def block_end(self):
         need = C.c_uint64(0)
         n = lib().zpaqgpu_block_end(self._h, None, 0, C.byref(need))
@@ -393,3 +442,113 @@ class Context:
             return None
         self._check(n)
         return b""
+
+
+class Multi:
+    """zpaqgpu_multi: several GPUs of one box behind one handle (one host thread + stream per device,
+    contiguous block ranges, results in block order)."""
+
+    def __init__(self, devices=None):
+        self._h = C.c_void_p()
+        if devices is None:
+            rc = lib().zpaqgpu_multi_init(C.byref(self._h), None, 0)
+        else:
+            arr = (C.c_int * len(devices))(*devices)
+            rc = lib().zpaqgpu_multi_init(C.byref(self._h), arr, len(devices))
+        if rc != OK:
+            self._h = None
+            raise ZpaqGpuError(rc, lib().zpaqgpu_strerror(rc).decode())
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().zpaqgpu_multi_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc < 0:
+            detail = lib().zpaqgpu_multi_last_error(self._h).decode(errors="replace")
+            raise ZpaqGpuError(int(rc), lib().zpaqgpu_strerror(int(rc)).decode() + (": " + detail if detail else ""))
+        return rc
+
+    def device_count(self):
+        return lib().zpaqgpu_multi_device_count(self._h)
+
+    def stats(self):
+        out = []
+        for k in range(self.device_count()):
+            s = MultiStats()
+            lib().zpaqgpu_multi_last_stats(self._h, k, C.byref(s))
+            d = {f: getattr(s, f) for f, _ in s._fields_ if f != "stats"}
+            d["stats"] = s.stats.as_dict()
+            out.append(d)
+        return out
+
+    def compress_blocks(self, level, blocks, names=None, comments=None):
+        n = len(blocks)
+        data = b"".join(bytes(b) for b in blocks)
+        off = (C.c_uint64 * (n + 1))()
+        pos = 0
+        for i, b in enumerate(blocks):
+            off[i] = pos
+            pos += len(b)
+        off[n] = pos
+        src = C.create_string_buffer(data, len(data)) if data else C.create_string_buffer(1)
+
+        def strs(v):
+            if v is None:
+                return None
+            arr = (C.c_char_p * max(n, 1))()
+            for i, x in enumerate(v):
+                arr[i] = x.encode() if isinstance(x, str) else x
+            return arr
+
+        a_names, a_comments = strs(names), strs(comments)
+        cap = len(data) + len(data) // 4 + 4096 * max(n, 1)
+        out_off = (C.c_uint64 * (n + 1))()
+        need = C.c_uint64(0)
+        for _ in range(2):
+            out = C.create_string_buffer(cap)
+            rc = lib().zpaqgpu_multi_compress_blocks(self._h, level, src, off, n, a_names, a_comments, out, cap,
+                                                     out_off, C.byref(need))
+            if rc == E_NOSPACE:
+                cap = need.value + 16
+                continue
+            self._check(rc)
+            raw = out.raw
+            return [raw[out_off[i]:out_off[i + 1]] for i in range(n)]
+        raise ZpaqGpuError(E_NOSPACE, "output sizing did not converge")
+
+    def decompress_archive(self, arc):
+        """(plaintext, [segment dict...], status), as Context.decompress_archive."""
+        arc = bytes(arc)
+        cap = max(4 * len(arc), 1 << 16)
+        seg_cap = 256
+        need, nseg = C.c_uint64(0), C.c_int(0)
+        for _ in range(4):
+            out = C.create_string_buffer(cap)
+            segs = (Segment * seg_cap)()
+            rc = lib().zpaqgpu_multi_decompress_archive(self._h, arc, len(arc), out, cap, C.byref(need), segs, seg_cap,
+                                                        C.byref(nseg))
+            if rc == E_NOSPACE:
+                cap = max(cap, need.value + 16)
+                seg_cap = max(seg_cap, nseg.value + 16)
+                continue
+            status = rc
+            if rc not in (OK, E_FORMAT, E_UNSUPPORTED):
+                self._check(rc)
+            res = []
+            for i in range(nseg.value):
+                s = segs[i]
+                name = arc[s.name_off:arc.index(b"\0", s.name_off)]
+                comment = arc[s.comment_off:arc.index(b"\0", s.comment_off)]
+                res.append(dict(filename=name.decode("latin1"), comment=comment.decode("latin1"),
+                                out_off=s.out_off, out_len=s.out_len, block_index=s.block_index,
+                                block_start=s.block_start, block_end=s.block_end, sha1_ok=s.sha1_ok))
+            return out.raw[:need.value], res, status
+        raise ZpaqGpuError(E_NOSPACE, "output sizing did not converge")

@@ -59,13 +59,18 @@ def default_context():
 
 class Compressor:
     """compressor.v:16-413.  Bytes are gathered per segment and the block is coded on the device
-    at end_block(); the bytes written to the Writer are identical to the reference's."""
+    at end_block(); the bytes written to the Writer are identical to the reference's.
 
-    def __init__(self, ctx=None):
+    batch=True is for callers that write many blocks one after the other (cmd/main.v:288-317, one block
+    per file): end_block() queues the block, the queue is coded in ONE launch when it is full or at
+    flush() -- which the caller adds before it closes the output (cmd/main.v:320).  Same bytes, same order."""
+
+    def __init__(self, ctx=None, batch=False):
         self._ctx = ctx or default_context()
         self._input = None
         self._output = None
         self._state = "start"
+        self._batch = batch
 
     def set_input(self, reader):
         self._input = reader
@@ -118,10 +123,24 @@ class Compressor:
     def end_block(self):
         if self._state != "block":
             return
+        if self._batch:
+            full = self._ctx._check(self._ctx.block_end_queue())
+            self._state = "start"
+            if full:
+                self.flush()
+            return
         data = self._ctx.block_end()
         if data and self._output is not None:
             self._output.write(data)
         self._state = "start"
+
+    def flush(self):
+        """Deliver the queued blocks (batch mode); a no-op otherwise."""
+        if self._state != "start":
+            return
+        data = self._ctx.flush()
+        if data and self._output is not None:
+            self._output.write(data)
 
 
 class Decompresser:

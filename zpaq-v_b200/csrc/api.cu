@@ -408,15 +408,10 @@ int run_compress(zpaqgpu_ctx *ctx, CompressJob &job) {
 
 std::string size_comment(u64 n) { return std::to_string(n) + " bytes"; }
 
-int compress_host(zpaqgpu_ctx *ctx, const Model &m, const uint8_t *in, const uint64_t *in_off, int n_blocks,
-                  const char *const *names, const char *const *comments, uint8_t *out, uint64_t out_cap,
-                  uint64_t *out_off, uint64_t *out_need) {
-    if (!ctx || n_blocks < 0 || (n_blocks > 0 && (!in_off || !out_off))) return ZPAQGPU_E_ARG;
-    if (n_blocks == 0) {
-        if (out_off) out_off[0] = 0;
-        if (out_need) *out_need = 0;
-        return ZPAQGPU_OK;
-    }
+// Host buffers -> archive bytes in ctx->out and block offsets in ctx->out_off (device): the upload and the
+// compression job, without the copy back.  *total receives the archive size.
+int compress_stage(zpaqgpu_ctx *ctx, const Model &m, const uint8_t *in, const uint64_t *in_off, int n_blocks,
+                   const char *const *names, const char *const *comments, u64 *total) {
     CK(cudaSetDevice(ctx->device));
     const u64 base = in_off[0], total_in = in_off[n_blocks] - base;
     if (total_in > 0 && !in) return ZPAQGPU_E_ARG;
@@ -457,19 +452,45 @@ int compress_host(zpaqgpu_ctx *ctx, const Model &m, const uint8_t *in, const uin
         job.d_out = static_cast<u8 *>(ctx->out.p), job.out_cap = ctx->out.cap;
         if ((rc = run_compress(ctx, job))) return rc;
     }
-    if (out_need) *out_need = job.total;
+    *total = job.total;
+    return ZPAQGPU_OK;
+}
+
+// The staged archive back to the host: `total` bytes to out, the n_blocks+1 offsets (plus `shift`) to out_off.
+int compress_fetch(zpaqgpu_ctx *ctx, int n_blocks, u64 total, uint8_t *out, uint64_t *out_off, u64 shift) {
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
     CK(cudaMemcpyAsync(out_off, ctx->out_off.p, 8 * size_t(n_blocks + 1), cudaMemcpyDeviceToHost, st));
-    if (job.total > out_cap) {
-        CK(cudaStreamSynchronize(st));
-        return ZPAQGPU_E_NOSPACE;
-    }
-    if (job.total && !out) return ZPAQGPU_E_ARG;
     CK(cudaEventRecord(ctx->ev[6], st));
-    if (job.total) CK(cudaMemcpyAsync(out, ctx->out.p, job.total, cudaMemcpyDeviceToHost, st));
+    if (total) CK(cudaMemcpyAsync(out, ctx->out.p, total, cudaMemcpyDeviceToHost, st));
     CK(cudaEventRecord(ctx->ev[7], st));
     CK(cudaStreamSynchronize(st));
     ctx->stats.d2h_ms = elapsed(ctx->ev[6], ctx->ev[7]);
+    if (shift)
+        for (int b = 0; b <= n_blocks; ++b) out_off[b] += shift;
     return ZPAQGPU_OK;
+}
+
+int compress_host(zpaqgpu_ctx *ctx, const Model &m, const uint8_t *in, const uint64_t *in_off, int n_blocks,
+                  const char *const *names, const char *const *comments, uint8_t *out, uint64_t out_cap,
+                  uint64_t *out_off, uint64_t *out_need) {
+    if (!ctx || n_blocks < 0 || (n_blocks > 0 && (!in_off || !out_off))) return ZPAQGPU_E_ARG;
+    if (n_blocks == 0) {
+        if (out_off) out_off[0] = 0;
+        if (out_need) *out_need = 0;
+        return ZPAQGPU_OK;
+    }
+    u64 total = 0;
+    int rc = compress_stage(ctx, m, in, in_off, n_blocks, names, comments, &total);
+    if (rc) return rc;
+    if (out_need) *out_need = total;
+    if (total > out_cap) {
+        CK(cudaMemcpyAsync(out_off, ctx->out_off.p, 8 * size_t(n_blocks + 1), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        return ZPAQGPU_E_NOSPACE;
+    }
+    if (total && !out) return ZPAQGPU_E_ARG;
+    return compress_fetch(ctx, n_blocks, total, out, out_off, 0);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -827,6 +848,7 @@ int decode_archive_dev(zpaqgpu_ctx *ctx, const uint8_t *arc, u64 len, std::vecto
     int seg_total = 0, block_index = 0;
     int status = ZPAQGPU_OK;
     size_t rec_at = 0;
+    ctx->walk_stopped = false;
     for (size_t i = 0; i < job.cand.size(); ++i) {
         const DecCandidate &c = job.cand[i];
         // a later find_block call restarts its rolling hashes at `pos`, so it only sees locators
@@ -835,6 +857,7 @@ int decode_archive_dev(zpaqgpu_ctx *ctx, const uint8_t *arc, u64 len, std::vecto
         if (c.group < 0) {
             // find_block returns false here and `for find_block {}` ends (cmd/main.v:349)
             status = c.group == -2 ? ZPAQGPU_E_UNSUPPORTED : ZPAQGPU_OK;
+            ctx->walk_stopped = true;
             break;
         }
         while (rec_at < job.recs.size() && job.recs[rec_at].block < u32(i)) ++rec_at;
@@ -854,10 +877,34 @@ int decode_archive_dev(zpaqgpu_ctx *ctx, const uint8_t *arc, u64 len, std::vecto
         if (c.res.status != ZPAQGPU_OK && status == ZPAQGPU_OK) status = c.res.status;
         pos = c.res.end_pos;
         ++block_index;
-        if (c.res.status != ZPAQGPU_OK) break;
+        if (c.res.status != ZPAQGPU_OK) {
+            ctx->walk_stopped = true;
+            break;
+        }
     }
     (void)seg_total;
     *d_plain = job.d_plain, *status_out = status, *total_out = total;
+    return ZPAQGPU_OK;
+}
+
+// Plaintext of the listed segments from the device arena to `out`, back to back in list order;
+// contiguous runs of the arena are merged into single copies.
+int plain_fetch(zpaqgpu_ctx *ctx, const std::vector<DecodedSeg> &list, const u8 *d_plain, uint8_t *out) {
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    CK(cudaEventRecord(ctx->ev[6], st));
+    u64 dst = 0;
+    for (size_t k = 0; k < list.size();) {
+        u64 src = list[k].src, run = list[k].seg.out_len;
+        size_t j = k + 1;
+        while (j < list.size() && list[j].src == src + run) run += list[j].seg.out_len, ++j;
+        if (run) CK(cudaMemcpyAsync(out + dst, d_plain + src, run, cudaMemcpyDeviceToHost, st));
+        dst += run;
+        k = j;
+    }
+    CK(cudaEventRecord(ctx->ev[7], st));
+    CK(cudaStreamSynchronize(st));
+    ctx->stats.d2h_ms = elapsed(ctx->ev[6], ctx->ev[7]);
     return ZPAQGPU_OK;
 }
 
@@ -1150,7 +1197,6 @@ int zpaqgpu_decompress_archive(zpaqgpu_ctx *ctx, const uint8_t *arc, uint64_t le
     u64 total = 0;
     int rc = decode_archive_dev(ctx, arc, len, list, &d_plain, &status, &total);
     if (rc) return rc;
-    cudaStream_t st = ctx->stream;
     const int seg_total = int(list.size());
     if (segs)
         for (int k = 0; k < seg_total && k < segs_cap; ++k) segs[k] = list[size_t(k)].seg;
@@ -1158,20 +1204,7 @@ int zpaqgpu_decompress_archive(zpaqgpu_ctx *ctx, const uint8_t *arc, uint64_t le
     if (n_segs) *n_segs = seg_total;
     if (total > out_cap || (segs && seg_total > segs_cap)) return ZPAQGPU_E_NOSPACE;
     if (total && !out) return ZPAQGPU_E_ARG;
-    // 5. plaintext back to the host: contiguous runs of the arena are merged into single copies
-    CK(cudaEventRecord(ctx->ev[6], st));
-    u64 dst = 0;
-    for (size_t k = 0; k < list.size();) {
-        u64 src = list[k].src, run = list[k].seg.out_len;
-        size_t j = k + 1;
-        while (j < list.size() && list[j].src == src + run) run += list[j].seg.out_len, ++j;
-        if (run) CK(cudaMemcpyAsync(out + dst, d_plain + src, run, cudaMemcpyDeviceToHost, st));
-        dst += run;
-        k = j;
-    }
-    CK(cudaEventRecord(ctx->ev[7], st));
-    CK(cudaStreamSynchronize(st));
-    ctx->stats.d2h_ms = elapsed(ctx->ev[6], ctx->ev[7]);
+    if ((rc = plain_fetch(ctx, list, d_plain, out))) return rc;
     return status;
     });
 }
@@ -1233,118 +1266,6 @@ int zpaqgpu_decompress_blocks_dev(zpaqgpu_ctx *ctx, const void *d_arc, const uin
     if (d_out_len) CK(cudaMemcpy(d_out_len, lens.data(), 8 * size_t(n_blocks), cudaMemcpyHostToDevice));
     if (n_bad) *n_bad = bad;
     return ZPAQGPU_OK;
-    });
-}
-
-// ---- streaming-shaped calls ----
-int zpaqgpu_block_begin_header(zpaqgpu_ctx *ctx, const uint8_t *header, int header_len) {
-    return zg::guarded<int>(ctx, [&]() -> int {
-    if (!ctx) return ZPAQGPU_E_ARG;
-    if (ctx->st_state != 2) return ZPAQGPU_E_STATE;  // compressor.v:80-82
-    const int rc = model_from_level_layout(header, header_len, ctx->st_model);
-    if (rc) return ctx->err = ctx->st_model.error, rc;
-    ctx->st_segs.clear();
-    ctx->st_has_done = false;
-    ctx->st_state = 0;
-    return ZPAQGPU_OK;
-    });
-}
-int zpaqgpu_block_begin(zpaqgpu_ctx *ctx, int level) {
-    return zg::guarded<int>(ctx, [&]() -> int {
-    const std::vector<uint8_t> h = level_header(level);
-    return zpaqgpu_block_begin_header(ctx, h.data(), int(h.size()));
-    });
-}
-int zpaqgpu_segment_begin(zpaqgpu_ctx *ctx, const char *filename, const char *comment) {
-    return zg::guarded<int>(ctx, [&]() -> int {
-    if (!ctx) return ZPAQGPU_E_ARG;
-    if (ctx->st_state != 0) return ZPAQGPU_E_STATE;  // compressor.v:213-215
-    PendingSeg s;
-    s.name = filename ? filename : "", s.comment = comment ? comment : "";
-    ctx->st_segs.push_back(std::move(s));
-    ctx->st_state = 1;
-    return ZPAQGPU_OK;
-    });
-}
-int zpaqgpu_segment_write(zpaqgpu_ctx *ctx, const uint8_t *data, uint64_t len) {
-    return zg::guarded<int>(ctx, [&]() -> int {
-    if (!ctx || (len && !data)) return ZPAQGPU_E_ARG;
-    if (ctx->st_state != 1) return ZPAQGPU_E_STATE;  // compressor.v:260-262
-    PendingSeg &s = ctx->st_segs.back();
-    s.called = true;
-    s.data.insert(s.data.end(), data, data + len);
-    return ZPAQGPU_OK;
-    });
-}
-int zpaqgpu_segment_end(zpaqgpu_ctx *ctx) {
-    if (!ctx) return ZPAQGPU_E_ARG;
-    if (ctx->st_state != 1) return ZPAQGPU_E_STATE;  // compressor.v:358-360
-    ctx->st_state = 0;
-    return ZPAQGPU_OK;
-}
-int64_t zpaqgpu_block_end(zpaqgpu_ctx *ctx, uint8_t *out, uint64_t cap, uint64_t *need) {
-    return zg::guarded<int64_t>(ctx, [&]() -> int64_t {
-    if (!ctx) return ZPAQGPU_E_ARG;
-    if (!ctx->st_has_done) {
-        if (ctx->st_state != 0) return ZPAQGPU_E_STATE;  // compressor.v:403-405
-        if (cudaSetDevice(ctx->device) != cudaSuccess) return ZPAQGPU_E_NODEVICE;
-        const Model &m = ctx->st_model;
-        const int n_segs = int(ctx->st_segs.size());
-        std::vector<uint8_t> &done = ctx->st_done;
-        done.clear();
-        if (n_segs == 0) {
-            // a block without segments is just its header and 0xFF (compressor.v:150-181, :409)
-            done = m.block_prefix;
-            done.push_back(0xFF);
-        } else {
-            u64 total_in = 0;
-            for (const PendingSeg &s : ctx->st_segs) total_in += s.data.size();
-            std::vector<uint8_t> flat;
-            flat.reserve(size_t(total_in));
-            CompressJob job;
-            job.model = &m;
-            job.blocks.push_back(EncBlock{0, u32(n_segs)});
-            u64 worst = m.block_prefix.size() + 64;
-            for (const PendingSeg &s : ctx->st_segs) {
-                SegSpec sp;
-                sp.name = s.name.c_str(), sp.comment = s.comment.c_str();
-                sp.in_off = flat.size(), sp.in_len = s.data.size(), sp.called = s.called;
-                flat.insert(flat.end(), s.data.begin(), s.data.end());
-                job.segs.push_back(sp);
-                worst += sp.in_len + sp.in_len / 4 + 2048 + s.name.size() + s.comment.size();
-            }
-            int rc;
-            if ((rc = ensure(ctx, ctx->in, std::max<u64>(total_in, 16)))) return rc;
-            if (total_in &&
-                cudaMemcpyAsync(ctx->in.p, flat.data(), total_in, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess)
-                return ZPAQGPU_E_CUDA;
-            if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) return ZPAQGPU_E_CUDA;
-            for (int attempt = 0; attempt < 2; ++attempt) {
-                if ((rc = ensure(ctx, ctx->out, worst))) return rc;
-                if ((rc = ensure(ctx, ctx->out_off, 16))) return rc;
-                job.d_in = static_cast<const u8 *>(ctx->in.p);
-                job.d_out = static_cast<u8 *>(ctx->out.p), job.out_cap = ctx->out.cap;
-                job.d_out_off = static_cast<u64 *>(ctx->out_off.p);
-                if ((rc = run_compress(ctx, job))) return rc;
-                if (job.fits) break;
-                worst = job.total;
-            }
-            if (!job.fits) return ZPAQGPU_E_NOSPACE;
-            done.resize(size_t(job.total));
-            if (job.total && cudaMemcpy(done.data(), ctx->out.p, job.total, cudaMemcpyDeviceToHost) != cudaSuccess)
-                return ZPAQGPU_E_CUDA;
-        }
-        ctx->st_has_done = true;
-    }
-    if (need) *need = ctx->st_done.size();
-    if (ctx->st_done.size() > cap || (!out && !ctx->st_done.empty())) return ZPAQGPU_E_NOSPACE;
-    if (!ctx->st_done.empty()) std::memcpy(out, ctx->st_done.data(), ctx->st_done.size());
-    const int64_t n = int64_t(ctx->st_done.size());
-    ctx->st_has_done = false;
-    ctx->st_done.clear();
-    ctx->st_segs.clear();
-    ctx->st_state = 2;
-    return n;
     });
 }
 

@@ -23,6 +23,11 @@ struct PendingSeg {
     bool called = false;  // compress() was called at least once
 };
 
+struct QueuedBlock {  // a finished block of the streaming-shaped calls
+    int model;            // index into zpaqgpu_ctx::st_models
+    std::vector<PendingSeg> segs;
+};
+
 struct SegSpec {  // one segment of a compression job
     const char *name, *comment;
     u64 in_off, in_len;
@@ -49,6 +54,7 @@ struct zpaqgpu_ctx {
     zg::u64 ws_limit = 0;
     int sm_count = 148;
     std::string err;
+    bool walk_stopped = false;  // the last archive walk ended before its last candidate (find_block false / bad block)
     zpaqgpu_stats stats{};
     // grow-only device buffers
     zg::DevBuf workspace, in, arena, out, desc, pay_len, digests, seg_size, out_off, modelblob, results,
@@ -60,11 +66,16 @@ struct zpaqgpu_ctx {
     // pinned host staging for small read-backs
     void *pinned = nullptr;
     size_t pinned_cap = 0;
-    // streaming-shaped state (compressor.v:6-8 state machine)
+    // streaming-shaped state (compressor.v:6-8 state machine), stream.cu
     int st_state = 2;  // 0 block, 1 segment, 2 start
-    zg::Model st_model;
-    std::vector<zg::PendingSeg> st_segs;
-    std::vector<uint8_t> st_done;  // finished block kept until the caller's buffer is large enough
+    int st_model = -1; // index into st_models of the block being filled
+    std::vector<zg::Model> st_models;        // distinct model headers of the queued blocks
+    std::vector<zg::PendingSeg> st_segs;     // segments of the block being filled
+    std::vector<zg::QueuedBlock> st_queue;   // finished blocks waiting for zpaqgpu_flush
+    zg::u64 st_queue_bytes = 0;
+    int st_batch_blocks = 1024;              // block_end_queue reports "full" at these limits
+    zg::u64 st_batch_bytes = 1ull << 30;
+    std::vector<uint8_t> st_done;  // coded bytes kept until the caller's buffer is large enough
     bool st_has_done = false;
 };
 
@@ -117,6 +128,13 @@ float elapsed(cudaEvent_t a, cudaEvent_t b);
 // blocks of segments, plaintext already on the device -> archive bytes on the device
 int run_compress(zpaqgpu_ctx *ctx, CompressJob &job);
 
+// Host buffers -> archive in ctx->out / ctx->out_off on the device (compress_stage), and the copy back
+// (compress_fetch; `shift` is added to every offset).  zpaqgpu_compress_blocks is one after the other; the
+// multi-device calls (multi.cu) run all stages first and fetch once every device's size is known.
+int compress_stage(zpaqgpu_ctx *ctx, const Model &m, const uint8_t *in, const uint64_t *in_off, int n_blocks,
+                   const char *const *names, const char *const *comments, u64 *total);
+int compress_fetch(zpaqgpu_ctx *ctx, int n_blocks, u64 total, uint8_t *out, uint64_t *out_off, u64 shift);
+
 // A decoded segment: the public record plus where its plaintext sits in the device arena.
 struct DecodedSeg {
     zpaqgpu_segment seg;
@@ -126,5 +144,8 @@ struct DecodedSeg {
 // find_block / find_filename meet them (decompressor.v:219-635).
 int decode_archive_dev(zpaqgpu_ctx *ctx, const uint8_t *arc, u64 len, std::vector<DecodedSeg> &segs,
                        const u8 **d_plain, int *status, u64 *total);
+
+// plaintext of the listed segments, device arena -> out, back to back in list order
+int plain_fetch(zpaqgpu_ctx *ctx, const std::vector<DecodedSeg> &list, const u8 *d_plain, uint8_t *out);
 
 }  // namespace zg
