@@ -550,6 +550,8 @@ def run_per_level(args, E):
         codec = DeviceCodec(E["z"], E["zb"], torch, dev, torch.cuda.current_stream().cuda_stream)
         try:
             total = nb * bb
+            if not data_np.flags.writeable:
+                data_np = data_np.copy()
             d_in = torch.from_numpy(data_np).to(dev)
             # a small pass first: module load, first-touch of the constant tables, buffer growth
             wb = min(nb, warm_blocks)

@@ -21,7 +21,8 @@ int ensure(zpaqgpu_ctx *ctx, DevBuf &b, size_t bytes) {
         CK(cudaFree(b.p));
         b.p = nullptr, b.cap = 0;
     }
-    size_t want = bytes + bytes / 8 + 4096;
+    // small buffers get 12.5 % head room against regrowth; the multi-gigabyte ones are sized exactly
+    size_t want = bytes + (bytes < (size_t(1) << 30) ? bytes / 8 : 0) + 4096;
     cudaError_t e = cudaMalloc(&b.p, want);
     if (e != cudaSuccess) {
         cudaGetLastError();
@@ -30,7 +31,11 @@ int ensure(zpaqgpu_ctx *ctx, DevBuf &b, size_t bytes) {
     }
     if (e != cudaSuccess) {
         cudaGetLastError();
-        ctx->err = "cudaMalloc of " + std::to_string(bytes) + " bytes failed";
+        size_t free_b = 0, total_b = 0;
+        cudaMemGetInfo(&free_b, &total_b);
+        cudaGetLastError();
+        ctx->err = "cudaMalloc of " + std::to_string(bytes) + " bytes failed (" + std::to_string(free_b) + " of " +
+                   std::to_string(total_b) + " bytes free)";
         return ZPAQGPU_E_NOMEM;
     }
     b.cap = want;
@@ -47,6 +52,22 @@ int ensure_pinned(zpaqgpu_ctx *ctx, size_t bytes) {
 }
 
 u64 align_up(u64 v, u64 a) { return (v + a - 1) / a * a; }
+
+// The two table buffers of a wave.  plan_tables budgets with both of them counted as free, so when either
+// has to grow both are released first: a large dense workspace kept from an earlier call must not sit
+// beside a new page pool (or the other way round).
+int ensure_tables(zpaqgpu_ctx *ctx, size_t ws_bytes, size_t pool_bytes) {
+    if (ws_bytes <= ctx->workspace.cap && pool_bytes <= ctx->pool.cap) return ZPAQGPU_OK;
+    CK(cudaStreamSynchronize(ctx->stream));
+    for (DevBuf *b : {&ctx->workspace, &ctx->pool})
+        if (b->p) {
+            CK(cudaFree(b->p));
+            b->p = nullptr, b->cap = 0;
+        }
+    int rc = ensure(ctx, ctx->workspace, std::max<size_t>(ws_bytes, 256));
+    if (rc == ZPAQGPU_OK && pool_bytes) rc = ensure(ctx, ctx->pool, pool_bytes);
+    return rc;
+}
 
 // The model on the device: header bytes, both component layouts, their fill lists, the images.
 struct ModelOnDev {
@@ -120,7 +141,11 @@ int plan_tables(zpaqgpu_ctx *ctx, const Model &m, int n_blocks, size_t other_byt
     if (!ctx->ws_limit && budget > other_bytes) budget -= std::min<u64>(other_bytes, budget / 2);
     const u64 dense_slots = m.ws_bytes ? budget / m.ws_bytes : u64(n_blocks);
     const bool can_page = chain && m.ws_bytes_paged > 0 && !force_dense && ctx->table_mode != ZPAQGPU_TABLES_DENSE;
-    const bool want_page = can_page && (ctx->table_mode == ZPAQGPU_TABLES_PAGED || dense_slots < u64(n_blocks));
+    // Dense waves are kept while one wave still holds enough blocks to fill the device (four per SM): a
+    // second wave costs nothing then, and incompressible blocks -- which touch every line and would run a
+    // page pool dry -- need no retry.  Paging is for models whose dense tables leave most SMs idle (-m4/-m5).
+    const u64 enough = std::min<u64>(u64(n_blocks), 4ull * u64(ctx->sm_count));
+    const bool want_page = can_page && (ctx->table_mode == ZPAQGPU_TABLES_PAGED || dense_slots < enough);
     if (want_page) {
         u64 ht_bytes = 0;
         for (const CompDesc &c : m.comps)
@@ -307,8 +332,7 @@ int run_compress(zpaqgpu_ctx *ctx, CompressJob &job) {
             for (int table_try = 0; table_try < 2; ++table_try) {
                 TablePlan tp;
                 if ((rc = plan_tables(ctx, m, n_blocks, arena_bytes, chain, force_dense, tp))) return rc;
-                if ((rc = ensure(ctx, ctx->workspace, u64(tp.slots) * tp.stride))) return rc;
-                if (tp.paged && (rc = ensure(ctx, ctx->pool, tp.pool_bytes))) return rc;
+                if ((rc = ensure_tables(ctx, u64(tp.slots) * tp.stride, tp.paged ? tp.pool_bytes : 0))) return rc;
                 // encoder: three warps per block, as many blocks per CTA as spreads the wave over all SMs
                 int wpc = 4;
                 if (chain) {
@@ -587,8 +611,8 @@ int run_decompress(zpaqgpu_ctx *ctx, DecompressJob &job, bool caller_owns_plain)
                         tp.slots = run;
                         if (!store) {
                             if ((rc = plan_tables(ctx, m, run, plain_bytes, chain, dense_only, tp))) return rc;
-                            if ((rc = ensure(ctx, ctx->workspace, u64(tp.slots) * tp.stride))) return rc;
-                            if (tp.paged && (rc = ensure(ctx, ctx->pool, tp.pool_bytes))) return rc;
+                            if ((rc = ensure_tables(ctx, u64(tp.slots) * tp.stride, tp.paged ? tp.pool_bytes : 0)))
+                                return rc;
                             ctx->stats.paged = tp.paged ? 1 : 0;
                             ctx->stats.workspace_bytes_per_block = tp.stride;
                         }
