@@ -54,7 +54,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=5, help="cap of the end-to-end timed steps (stated in the line)")
-    ap.add_argument("--per-level", default="1,3,4,5,jidac", help="extra configurations after the headline")
+    ap.add_argument("--per-level", default="1,3,4,5,jidac,generic", help="extra configurations after the headline")
     ap.add_argument("--no-per-level", action="store_true")
     ap.add_argument("--cfg3-blocks", type=int, default=8192, help="cfg 3: blocks of 1 MiB over ALL ranks")
     ap.add_argument("--cfg4-blocks", type=int, default=1024, help="cfg 4: blocks of 4 MiB per rank")
@@ -628,13 +628,60 @@ def run_per_level(args, E):
                 del data
             elif key == "jidac" and rank == 0:
                 out["jidac_add"] = run_jidac(args, E)
+            elif key == "generic" and rank == 0:
+                out["generic"] = run_generic(args, E)
         except SystemExit:
             raise
         except Exception as ex:  # a configuration that cannot run is reported, never silently dropped
-            out["m" + key if key != "jidac" else "jidac_add"] = {"error": "%s: %s" % (type(ex).__name__, ex)}
+            name = {"jidac": "jidac_add", "generic": "generic"}.get(key, "m" + key)
+            out[name] = {"error": "%s: %s" % (type(ex).__name__, ex)}
             torch.cuda.empty_cache()
     E["barrier"]()
     return out
+
+
+def run_generic(args, E):
+    """a header outside the -m1..-m5 shape (ICM, MATCH, MIX2, ISSE, SSE + a HASH/HASHD program)
+    through the generic path: the warp kernel (component per lane, warp-uniform ZPAQL) beside the one-lane
+    kernel it replaces (ZPAQGPU_GENERIC=lane0), same blocks, kernel time from CUDA events."""
+    datagen, z = E["datagen"], E["z"]
+    import oracle_binding as ob
+    hdr = bytes([3, 10, 0, 0, 5, 3, 14, 4, 12, 14, 6, 10, 0, 1, 20, 255, 8, 12, 2, 9, 10, 3, 32, 100, 0,
+                 104, 17, 28, 59, 112, 25, 60, 25, 59, 112, 25, 65, 112, 25, 112, 56, 0])
+    nb, bb = 592, 32768
+    text = E["text"]
+    blocks = [text[k * bb:(k + 1) * bb].tobytes() for k in range(nb)]
+    res = {"what": "custom header icm_match_mix2_sse (5 components, 16-op HCOMP), %d x %d KiB text blocks, host "
+                   "buffers" % (nb, bb // 1024), "blocks": nb, "block_bytes": bb}
+    arcs = {}
+    for name, env in (("warp", None), ("lane0", "lane0")):
+        if env:
+            os.environ["ZPAQGPU_GENERIC"] = env
+        else:
+            os.environ.pop("ZPAQGPU_GENERIC", None)
+        ctx = z.Context(E["dev"].index)
+        try:
+            ctx.compress_blocks(0, blocks[:8], header=hdr)
+            got = ctx.compress_blocks(0, blocks, header=hdr)
+            st_c = ctx.stats()
+            plain, segs, status = ctx.decompress_archive(b"".join(got))
+            st_d = ctx.stats()
+            if status != 0 or plain != b"".join(blocks):
+                raise SystemExit("generic %s: round trip mismatch" % name)
+            arcs[name] = got
+            res[name] = {"compress_kernel_ms": round(st_c["codec_ms"], 2), "decompress_kernel_ms": round(st_d["codec_ms"], 2),
+                         "compress_kernel_mb_s": round(nb * bb / st_c["codec_ms"] / 1e3, 2),
+                         "decompress_kernel_mb_s": round(nb * bb / st_d["codec_ms"] / 1e3, 2), "kernel": st_c["kernel"]}
+        finally:
+            ctx.close()
+    os.environ.pop("ZPAQGPU_GENERIC", None)
+    res["speedup_over_lane0"] = {"compress": round(res["lane0"]["compress_kernel_ms"] / res["warp"]["compress_kernel_ms"], 2),
+                                 "decompress": round(res["lane0"]["decompress_kernel_ms"] / res["warp"]["decompress_kernel_ms"], 2)}
+    idx = [0, 77, 300, 591]
+    res["byte_identical_to_oracle"] = all(arcs["warp"][k] == arcs["lane0"][k] == ob.compress_block(0, blocks[k], "", "", header=hdr)
+                                          for k in idx)
+    res["parity_blocks"] = idx
+    return res
 
 
 def run_jidac(args, E):

@@ -37,6 +37,47 @@ def test_generic_components_match_oracle(gpu_ctx, name):
     assert status == 0 and plain == b"".join(blocks) and all(s["sha1_ok"] == 1 for s in segs)
 
 
+@pytest.mark.parametrize("name", ["icm_match_mix2_sse", "forward_refs", "twenty", "vm_branches"])
+def test_generic_warp_kernel_equals_one_lane_kernel(name, monkeypatch):
+    """The warp program (component per lane, levels, MIX as a warp dot product, warp-uniform ZPAQL) against
+    the one-lane kernel it replaces and the oracle: multi-segment blocks included (tables persist, Q17)."""
+    import zpaq_v_b200 as z
+    hdr = bytes(CUSTOM_HEADERS[name])
+    blocks = [datagen.text(20000, 91), datagen.structured(9000), datagen.random_bytes(3000), b"", b"a" * 5000]
+    want = [ob.compress_block(0, b, "n%d" % k, "c", header=hdr) for k, b in enumerate(blocks)]
+    got = {}
+    for variant in ("warp", "lane0"):
+        if variant == "lane0":
+            monkeypatch.setenv("ZPAQGPU_GENERIC", "lane0")
+        else:
+            monkeypatch.delenv("ZPAQGPU_GENERIC", raising=False)
+        ctx = z.Context()
+        try:
+            got[variant] = ctx.compress_blocks(0, blocks, names=["n%d" % k for k in range(len(blocks))],
+                                               comments=["c"] * len(blocks), header=hdr)
+            assert ctx.stats()["kernel"] == 1
+            plain, segs, status = ctx.decompress_archive(b"".join(want))
+            assert status == 0 and plain == b"".join(blocks) and all(s["sha1_ok"] == 1 for s in segs)
+            # two segments in one block: component tables, M, H and the VM registers carry over
+            assert ctx.block_begin(header=hdr) == 0
+            for nm, data in (("s1", blocks[0][:7000]), ("s2", blocks[1][:5000])):
+                assert ctx.segment_begin(nm, "") == 0 and ctx.segment_write(data) == 0 and ctx.segment_end() == 0
+            two = ctx.block_end()
+            c = ob.Compressor()
+            c.start_block_header(hdr)
+            for nm, data in (("s1", blocks[0][:7000]), ("s2", blocks[1][:5000])):
+                c.set_input(data)
+                c.start_segment(nm, "")
+                while c.compress(65536):
+                    pass
+                c.end_segment()
+            c.end_block()
+            assert two == c.output()
+        finally:
+            ctx.close()
+    assert got["warp"] == want and got["lane0"] == want
+
+
 @pytest.mark.parametrize("kernel", [1, 2])
 @pytest.mark.parametrize("level", [0, 1, 2, 4])
 def test_multisegment_block_streaming_api(gpu_ctx, level, kernel):

@@ -201,6 +201,19 @@ CUSTOM_HEADERS = {
     "vm_branches": [2, 6, 0, 0, 2, 2, 14, 20, 8, 12, 0, 0,
                     # a>N jt: exercise compare, conditional jump (Q5 offsets), arithmetic, r[] file
                     104, 17, 239, 96, 39, 2, 135, 7, 55, 3, 7, 3, 151, 5, 28, 112, 25, 60, 56, 0],
+    # wiring the reference accepts because it only checks j < n (predictor.v:575-631): inputs that come LATER in
+    # the header (their prediction is the previous bit's), a MIX that contains itself, a MIX2 fed by itself, two
+    # MIX components.  0 ICM, 1 AVG(2,0), 2 CM, 3 ISSE(j=5), 4 MIX(0..5), 5 ICM, 6 MIX2(4,6), 7 MIX(3..6)
+    "forward_refs": [3, 8, 0, 0, 8, 3, 12, 5, 2, 0, 100, 2, 14, 8, 8, 12, 5, 7, 8, 0, 6, 24, 255, 3, 10,
+                     6, 8, 4, 6, 16, 0, 7, 0, 3, 4, 12, 0, 0,
+                     96, 4, 28, 59, 112, 25, 10, 59, 112, 25, 10, 59, 112, 25, 59, 112, 25, 59, 112, 25, 60, 25, 112, 25,
+                     112, 56, 0],
+    # twenty components of every type, one per lane of the warp kernel: 8 ICM, an ISSE chain and a side ISSE,
+    # MATCH, 2 CM, AVG, SSE, a 17-input MIX, MIX2, final SSE
+    "twenty": ([5, 10, 0, 0, 20] + [3, 10, 3, 11, 3, 12, 3, 10, 3, 11, 3, 12, 3, 10, 3, 11]
+               + [8, 11, 0, 8, 11, 8, 8, 10, 9, 8, 10, 3] + [4, 12, 14] + [2, 12, 20, 2, 14, 255] + [5, 10, 11, 128]
+               + [9, 8, 15, 16, 64] + [7, 8, 0, 17, 20, 255] + [6, 10, 16, 17, 24, 255] + [9, 10, 18, 32, 255] + [0]
+               + [96, 4, 28] + [59, 112, 25, 10] * 6 + [59, 112, 25] * 8 + [60, 25] * 3 + [59, 112, 25] * 3 + [56, 0]),
 }
 
 

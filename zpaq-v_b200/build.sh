@@ -6,7 +6,7 @@ set -e
 cd "$(dirname "$0")"
 NVCC=${NVCC:-nvcc}
 FLAGS="-std=c++17 -O3 -gencode arch=compute_100a,code=sm_100a -lineinfo -Xcompiler -fPIC,-ffp-contract=off,-fvisibility=hidden"
-CU="kernels_generic kernels_chain kernels_dectree kernels_encpipe kernels_aux api stream multi jidac"
+CU="kernels_generic kernels_genwarp kernels_chain kernels_dectree kernels_encpipe kernels_aux api stream multi jidac"
 mkdir -p build
 pids=""
 for f in $CU; do

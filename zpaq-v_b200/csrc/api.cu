@@ -361,6 +361,8 @@ int run_compress(zpaqgpu_ctx *ctx, CompressJob &job) {
                             ctx->err = "no chain kernel instantiation for this model";
                             return ZPAQGPU_E_UNSUPPORTED;
                         }
+                    } else if (ctx->generic_warp && genwarp_supports(m)) {
+                        if (!launch_encode_genwarp(ea, st)) return ctx->err = "generic warp kernel launch", ZPAQGPU_E_CUDA;
                     } else {
                         k_encode_generic<<<(n + 3) / 4, 128, 0, st>>>(ea);
                     }
@@ -652,6 +654,9 @@ int run_decompress(zpaqgpu_ctx *ctx, DecompressJob &job, bool caller_owns_plain)
                                         ctx->err = "no chain kernel instantiation for this model";
                                         return ZPAQGPU_E_UNSUPPORTED;
                                     }
+                                } else if (ctx->generic_warp && genwarp_supports(m)) {
+                                    if (!launch_decode_genwarp(da, st))
+                                        return ctx->err = "generic warp kernel launch", ZPAQGPU_E_CUDA;
                                 } else {
                                     k_decode_generic<<<(cnt + 3) / 4, 128, 0, st>>>(da);
                                 }
@@ -974,6 +979,7 @@ int zpaqgpu_init(zpaqgpu_ctx **out, int device) {
     if (const char *v = std::getenv("ZPAQGPU_PULL")) ctx->pull_how = std::atoi(v) & 3;
     if (const char *v = std::getenv("ZPAQGPU_GUESS")) ctx->guess = std::max(0, std::min(4, std::atoi(v)));
     if (const char *v = std::getenv("ZPAQGPU_ENC_FLAGS")) ctx->enc_l1_pull = std::atoi(v) != 0;
+    if (const char *v = std::getenv("ZPAQGPU_GENERIC")) ctx->generic_warp = std::strcmp(v, "lane0") != 0;
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->sm_count = prop.multiProcessorCount;
     bool ok = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) == cudaSuccess &&

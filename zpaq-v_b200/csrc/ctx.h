@@ -48,6 +48,7 @@ struct zpaqgpu_ctx {
     bool enc_l1_pull = true;   // ZPAQGPU_ENC_FLAGS=0: the encoder's history warp does not pull the next slot line into L1
     int pull_how = 0;          // ZPAQGPU_PULL: how (experiments)
     int guess = 1;             // ZPAQGPU_GUESS=n: the two-warp decoder pulls the n (0, 1, 2, 4) likeliest next slot lines a nibble early
+    bool generic_warp = true;  // ZPAQGPU_GENERIC=lane0: the one-lane generic kernels also for headers the warp kernel takes (A/B)
     bool spec_probe = true;    // ZPAQGPU_SPEC_PROBE=0: the chain decoders probe only once a nibble is complete
     int decoder = 1;           // ZPAQGPU_DECODER in the environment: serial (0, one bit at a time), tree (1, one warp per
                                // block), tree2 (2, two warps per block; the default where the model allows it)

@@ -44,6 +44,12 @@ struct DecodeArgs {
 __global__ void k_encode_generic(EncodeArgs A);
 __global__ void k_decode_generic(DecodeArgs A);
 
+// warp program for any header with up to 32 components (kernels_genwarp.cu): component i on lane i,
+// warp-uniform ZPAQL interpreter.  The one-lane kernels above remain for headers with more components.
+bool genwarp_supports(const Model &m);
+bool launch_encode_genwarp(const EncodeArgs &A, cudaStream_t s);
+bool launch_decode_genwarp(const DecodeArgs &A, cudaStream_t s);
+
 // specialised ICM + ISSE chain (+ MIX2): return false when no instantiation fits the model.
 // Encoder (kernels_encpipe.cu): three warps per block; decoder (kernels_chain.cu): one warp per block.
 bool launch_encode_pipe3(const Model &m, const EncodeArgs &A, int blocks_per_cta, cudaStream_t s);

@@ -350,6 +350,26 @@ int build_layout(Model &m, bool paged) {
             break;
         }
     }
+    // evaluation levels (predictor.v:536-668 evaluates in index order: only inputs j < i are of this bit)
+    for (int i = 0; i < m.n; ++i) {
+        CompDesc &c = comps_out[size_t(i)];
+        int deepest = -1;
+        auto dep = [&](int j) {
+            if (j >= 0 && j < i) deepest = std::max(deepest, int(comps_out[size_t(j)].level));
+        };
+        switch (c.type) {
+        case C_AVG: dep(c.a), dep(c.b); break;
+        case C_MIX2: dep(int(c.p[0])), dep(int(c.p[1])); break;
+        case C_ISSE: case C_SSE: dep(c.b); break;
+        case C_MIX:
+            for (int l = 0; l < c.limit; ++l) dep(c.b + l);
+            break;
+        default: break;
+        }
+        const bool reads_others = c.type == C_AVG || c.type == C_MIX2 || c.type == C_ISSE || c.type == C_SSE ||
+                                  c.type == C_MIX;
+        c.level = reads_others ? deepest + 1 + (deepest < 0 ? 1 : 0) : 0;
+    }
     // ZPAQL memory (zpaql.v:74-96): allocated only for 0 < bits < 32
     const int hh = len >= 2 ? hd[0] : 0, hm = len >= 2 ? hd[1] : 0;
     if (hh > 26 || hm > 30) return m.error = "H/M array too large", ZPAQGPU_E_UNSUPPORTED;

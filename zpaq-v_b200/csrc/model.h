@@ -25,6 +25,8 @@ struct CompDesc {
     uint32_t ht_len;             // bytes
     uint64_t a16_off;            // MIX2 weights (u16)
     uint32_t a16_len;
+    int32_t level;               // 0: needs no other component's prediction; else 1 + the deepest input in
+                                 // front of it (warp kernel: components of one level are evaluated together)
 };
 
 constexpr uint32_t kPageBytes = 256;   // 4 hash lines of 64 bytes
