@@ -4,8 +4,11 @@
 //
 // Mapping (sm_100a), one ZPAQ block per warp:
 //  * COMPONENT i LIVES ON LANE i: its Component fields (a, b, c, limit, cxt), its context hash h[i], its
-//    prediction p[i] and its table pointers sit in that lane's registers; only the tables themselves (cm,
-//    ht, a16) are in the block's HBM workspace.
+//    prediction p[i], the 16-byte hash slot of the current nibble (ICM/ISSE: loaded at the nibble boundary,
+//    bit-history states read and replaced in registers, written back at the next boundary) and its table
+//    pointers sit in that lane's registers.  The small adaptive tables (ICM cm[256], ISSE cm[512]) are
+//    copied into the warp's shared memory while they fit its budget; the large ones (hash tables, CM, MIX,
+//    MIX2, SSE, MATCH) stay in the block's HBM workspace.
 //  * predict (predictor.v:536-668) runs in two parts.  FETCH: every lane does what does not depend on
 //    another component -- the hash-slot search of ICM/ISSE (find_ht, three candidates of one 64-byte line),
 //    the bit-history state, the table entry, the MIX2 weight, CONS/CM/ICM/MATCH predictions -- so the
@@ -34,6 +37,14 @@ constexpr unsigned kAll = 0xFFFFFFFFu;
 constexpr int kWarpsPerCta = 4;
 constexpr size_t kConstBytes = 32768 * 2 + 4096 * 2 + 512;  // stretch_pad, squash_pad, next-state pairs
 constexpr size_t kVmBytes = 4096;                            // per warp: R (1 KiB) + H and M when they fit
+constexpr size_t kTabBytes = 24576;                          // per warp: ICM / ISSE adaptive tables
+constexpr size_t kWarpBytes = kVmBytes + kTabBytes;
+
+__device__ __forceinline__ uint4 ldg128(const u8 *p) {
+    uint4 v;
+    asm volatile("ld.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
+}
 
 // ------------------------------------------------------------------------------------------
 // ZPAQL, warp-uniform
@@ -211,7 +222,10 @@ struct GenW {
     u32 cm_len, ht_len, q0, q1, q2, q3;
     i32 ja, jb;            // the lanes this component reads (AVG j,k; MIX2 j,k; ISSE/SSE j)
     bool va, vb;           // ... and whether they name a component (j < n)
-    i32 e0, e1;            // fetched table entry (ISSE weights, MIX2 weight, ...)
+    i32 e0, e1;            // fetched table entry (ISSE weights, MIX2 weight, CM / SSE cells)
+    uint4 sl;              // ICM / ISSE: the hash slot of the current nibble
+    u8 *slot_at;           // ... and where it lives in the table (nullptr: none yet)
+    bool sse_ok, sse_hi;   // SSE: e0/e1 hold cm[idx], cm[idx+1] of this bit; the cell update will touch is the second
     // ---- uniform ----
     i32 n, n_levels, lane;
     u32 c8, hmap4, h_len;
@@ -252,7 +266,31 @@ struct GenW {
             va = j < n, vb = k < n;
             ja = va ? j : 0, jb = vb ? k : 0;
         }
+        sl = make_uint4(0, 0, 0, 0), slot_at = nullptr, sse_ok = sse_hi = false;
         n_levels = __reduce_max_sync(kAll, act ? lvl : 0) + 1;
+        {   // ICM cm[256] / ISSE cm[512] into the warp's shared memory while the budget lasts (index order)
+            const u32 need = (act && type == C_ICM) ? 1024u : (act && type == C_ISSE) ? 2048u : 0u;
+            u32 incl = need;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const u32 up = __shfl_up_sync(kAll, incl, d);
+                if (lane >= d) incl += up;
+            }
+            const u32 at = incl - need;
+            const bool in_smem = need != 0 && at + need <= u32(kTabBytes);
+            u32 *dst = reinterpret_cast<u32 *>(smem_vm + kVmBytes + at);
+            for (int i = 0; i < n; ++i) {
+                const u32 words = __shfl_sync(kAll, in_smem ? need / 4 : 0u, i);
+                if (!words) continue;
+                const u64 from = __shfl_sync(kAll, u64(reinterpret_cast<uintptr_t>(cm)), i);
+                const u64 to = __shfl_sync(kAll, u64(reinterpret_cast<uintptr_t>(dst)), i);
+                const u32 *srcp = reinterpret_cast<const u32 *>(static_cast<uintptr_t>(from));
+                u32 *dstp = reinterpret_cast<u32 *>(static_cast<uintptr_t>(to));
+                for (u32 k = lane; k < words; k += 32) dstp[k] = srcp[k];
+            }
+            __syncwarp();
+            if (in_smem) cm = dst;
+        }
         // ZPAQL state (zpaql.v:74-96); cleared by the workspace memset / here for the shared part
         h_len = M.h_len;
         vm.lane = lane;
@@ -279,19 +317,35 @@ struct GenW {
         h = 0;
     }
 
-    // predictor.v:495-532: the three candidates are requested together, the choice is made from registers
-    __device__ __forceinline__ i32 find_slot(i32 sizebits, u32 key) {
+    // Predictor.find_ht (predictor.v:495-532) at a nibble boundary.  The slot of the previous nibble goes back
+    // to its table first (the reference updates the table in place; nobody but this lane reads this table),
+    // the three candidates of the line are requested together and the choice is made from registers.  An
+    // evicted slot is cleared in the registers; the table sees it at the next write-back.
+    __device__ __forceinline__ void probe(i32 sizebits, u32 key) {
+        if (slot_at) *reinterpret_cast<uint4 *>(slot_at) = sl;
         const u32 chk = (key >> sizebits) & 255u;
-        const u32 h0 = (key * 16u) & (ht_len - 16u), h1 = h0 ^ 16u, h2 = h0 ^ 32u;
-        const u32 w0 = *reinterpret_cast<const u16 *>(ht + h0), w1 = *reinterpret_cast<const u16 *>(ht + h1),
-                  w2 = *reinterpret_cast<const u16 *>(ht + h2);
-        if ((w0 & 255u) == chk) return i32(h0);
-        if ((w1 & 255u) == chk) return i32(h1);
-        if ((w2 & 255u) == chk) return i32(h2);
-        const u32 p0 = w0 >> 8, p1 = w1 >> 8, p2 = w2 >> 8;
-        const u32 victim = (p0 <= p1 && p0 <= p2) ? h0 : (p1 < p2 ? h1 : h2);
-        *reinterpret_cast<uint4 *>(ht + victim) = make_uint4(chk, 0u, 0u, 0u);
-        return i32(victim);
+        const u32 h0 = (key * 16u) & (ht_len - 16u);
+        u8 *b0 = ht + h0, *b1 = ht + (h0 ^ 16u), *b2 = ht + (h0 ^ 32u);
+        const uint4 s0 = ldg128(b0), s1 = ldg128(b1), s2 = ldg128(b2);
+        const bool m0 = (s0.x & 255u) == chk, m1 = (s1.x & 255u) == chk, m2 = (s2.x & 255u) == chk;
+        const u32 p0 = (s0.x >> 8) & 255u, p1 = (s1.x >> 8) & 255u, p2 = (s2.x >> 8) & 255u;
+        u8 *victim = (p0 <= p1 && p0 <= p2) ? b0 : (p1 < p2 ? b1 : b2);
+        const bool hit = m0 | m1 | m2;
+        slot_at = m0 ? b0 : m1 ? b1 : m2 ? b2 : victim;
+        const uint4 pick = m0 ? s0 : (m1 ? s1 : s2);
+        sl.x = hit ? pick.x : chk, sl.y = hit ? pick.y : 0u, sl.z = hit ? pick.z : 0u, sl.w = hit ? pick.w : 0u;
+    }
+    // byte i (1..15) of the slot registers: the bit-history state of tree node i (predictor.v:561, :622)
+    __device__ __forceinline__ u32 slot_state(u32 i) const {
+        const u32 w = i < 8 ? (i < 4 ? sl.x : sl.y) : (i < 12 ? sl.z : sl.w);
+        return (w >> ((i & 3u) * 8u)) & 255u;
+    }
+    __device__ __forceinline__ void slot_set(u32 i, u32 old_state, u32 new_state) {
+        const u32 d = (old_state ^ new_state) << ((i & 3u) * 8u);
+        if (i < 4) sl.x ^= d;
+        else if (i < 8) sl.y ^= d;
+        else if (i < 12) sl.z ^= d;
+        else sl.w ^= d;
     }
 
     // p[j] as component `lane` sees it during predict: this bit's value when j is in front of it, else
@@ -310,11 +364,12 @@ struct GenW {
             case C_CONS: p = (a - 128) * 16; break;
             case C_CM:
                 cxt = h ^ hmap4;
-                p = stretch(i32(cm[cxt & (cm_len - 1)] >> 17));
+                e0 = i32(cm[cxt & (cm_len - 1)]);
+                p = stretch(i32(u32(e0) >> 17));
                 break;
             case C_ICM:
-                if (nibble) c = find_slot(a + 2, h + 16u * c8);
-                cxt = ht[c + i32(hmap4 & 15)];
+                if (nibble) probe(a + 2, h + 16u * c8);
+                cxt = slot_state(hmap4 & 15u);
                 p = stretch(i32(cm[cxt] >> 8));
                 break;
             case C_MATCH:
@@ -334,8 +389,8 @@ struct GenW {
                 cxt = u32((i32(h) + (i32(c8) & i32(q1))) & (c - 1));
                 break;
             case C_ISSE: {
-                if (nibble) c = find_slot(a + 2, h + 16u * c8);
-                cxt = ht[c + i32(hmap4 & 15)];
+                if (nibble) probe(a + 2, h + 16u * c8);
+                cxt = slot_state(hmap4 & 15u);
                 const uint2 w = *reinterpret_cast<const uint2 *>(cm + cxt * 2);
                 e0 = i32(w.x), e1 = i32(w.y);
                 break;
@@ -360,13 +415,16 @@ struct GenW {
                     const i32 wt = pq & 63;
                     pq >>= 6;
                     const i32 idx = i32(cxt) + pq;
-                    if (idx >= 0 && idx + 1 < i32(cm_len)) {
-                        const i32 p1 = i32(cm[idx] >> 10), p2 = i32(cm[idx + 1] >> 10);
+                    sse_ok = idx >= 0 && idx + 1 < i32(cm_len);
+                    if (sse_ok) {
+                        e0 = i32(cm[idx]), e1 = i32(cm[idx + 1]);
+                        const i32 p1 = i32(u32(e0) >> 10), p2 = i32(u32(e1) >> 10);
                         p = stretch((p1 * (64 - wt) + p2 * wt) >> 13);
                     } else {
                         p = 0;
                     }
                     cxt = u32(idx) + u32(wt >> 5);
+                    sse_hi = (wt >> 5) != 0;
                     break;
                 }
                 default: break;
@@ -400,7 +458,7 @@ struct GenW {
             switch (type) {
             case C_CM: {
                 const u32 idx = cxt & (cm_len - 1);
-                const u32 pn = cm[idx];
+                const u32 pn = u32(e0);  // cm[idx] as predict read it
                 const i32 count = i32(pn & 0x3ff);
                 const i32 err = t - i32(pn >> 17);
                 const i32 upd = i32(u32(err) * u32(dt[count])) & -1024;  // wraps like V int
@@ -408,7 +466,7 @@ struct GenW {
                 break;
             }
             case C_ICM: {
-                ht[c + i32(hmap4 & 15)] = nex[(cxt & 255u) * 2 + u32(y)];
+                slot_set(hmap4 & 15u, cxt, nex[(cxt & 255u) * 2 + u32(y)]);
                 const u32 v = cm[cxt];
                 cm[cxt] = u32(i32(v) + ((t - i32(v >> 8)) >> 2));
                 break;
@@ -443,7 +501,7 @@ struct GenW {
             case C_MIX2: {
                 const i32 err = ((t - squash(p)) * i32(q2)) >> 5;
                 if (va && vb) {
-                    const i32 w = i32(a16[cxt]) + ((err * (pj - pk) + 4096) >> 13);
+                    const i32 w = e0 + ((err * (pj - pk) + 4096) >> 13);  // e0 = a16[cxt] as predict read it
                     a16[cxt] = u16(max(0, min(65535, w)));
                 }
                 break;
@@ -451,16 +509,17 @@ struct GenW {
             case C_ISSE: {
                 const i32 err = t - squash(p);
                 if (va) {
-                    const i32 w0 = d_clamp512k(i32(cm[cxt * 2]) + ((err * pj + 4096) >> 13));
-                    const i32 w1 = d_clamp512k(i32(cm[cxt * 2 + 1]) + ((err + 16) >> 5));
+                    const i32 w0 = d_clamp512k(e0 + ((err * pj + 4096) >> 13));
+                    const i32 w1 = d_clamp512k(e1 + ((err + 16) >> 5));
                     *reinterpret_cast<uint2 *>(cm + cxt * 2) = make_uint2(u32(w0), u32(w1));
                 }
-                ht[c + i32(hmap4 & 15)] = nex[(cxt & 255u) * 2 + u32(y)];
+                slot_set(hmap4 & 15u, cxt, nex[(cxt & 255u) * 2 + u32(y)]);
                 break;
             }
             case C_SSE: {
                 const u32 idx = cxt & (cm_len - 1);
-                u32 v = cm[idx];
+                // in range, cxt is idx or idx + 1 of predict: the cell is already in e0 / e1
+                u32 v = sse_ok ? u32(sse_hi ? e1 : e0) : cm[idx];
                 const i32 err = t - i32(v >> 17);
                 const i32 count = i32(v) & 1023;
                 if (count < limit) v = u32(i32(v) + ((err * (limit - count) + 4096) >> 13) + 1);
@@ -566,7 +625,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) k_encode_genwarp(EncodeArgs
     if (warp >= A.n_blocks) return;
     GenW g;
     g.block_init(A.model, A.workspace + u64(warp) * A.model.ws_bytes, A.tables, smem,
-                 smem + kConstBytes + size_t(wic) * kVmBytes);
+                 smem + kConstBytes + size_t(wic) * kWarpBytes);
     const EncBlock blk = A.blocks[A.order[A.first_block + warp]];
     for (u32 s = 0; s < blk.n_seg; ++s) {
         const EncSeg seg = A.segs[blk.first_seg + s];
@@ -605,7 +664,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) k_decode_genwarp(DecodeArgs
     const int bi = int(A.order[A.first_block + warp]);
     GenW g;
     g.block_init(A.model, A.workspace + u64(warp) * A.model.ws_bytes, A.tables, smem,
-                 smem + kConstBytes + size_t(wic) * kVmBytes);
+                 smem + kConstBytes + size_t(wic) * kWarpBytes);
     const DecBlock blk = A.blocks[bi];
     SourceW in{A.arc, blk.arc_pos, A.arc_len};
     DecBlockOut res;
@@ -694,7 +753,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) k_decode_genwarp(DecodeArgs
 // ------------------------------------------------------------------------------------------
 bool genwarp_supports(const Model &m) { return m.n >= 1 && m.n <= 32; }
 
-static size_t genwarp_smem() { return kConstBytes + size_t(kWarpsPerCta) * kVmBytes; }
+static size_t genwarp_smem() { return kConstBytes + size_t(kWarpsPerCta) * kWarpBytes; }
 
 bool launch_encode_genwarp(const EncodeArgs &A, cudaStream_t s) {
     if (cudaFuncSetAttribute(k_encode_genwarp, cudaFuncAttributeMaxDynamicSharedMemorySize, int(genwarp_smem())) !=
