@@ -355,7 +355,7 @@ int run_compress(zpaqgpu_ctx *ctx, CompressJob &job) {
                     ea.in = job.d_in, ea.arena = static_cast<u8 *>(ctx->arena.p);
                     ea.blocks = d_blocks, ea.segs = d_esegs, ea.pay_len = static_cast<u64 *>(ctx->pay_len.p);
                     ea.order = d_order, ea.first_block = first, ea.n_blocks = n;
-                    ea.flags = ctx->enc_l1_pull ? 1 : 0;
+                    ea.flags = ctx->enc_flags;
                     if (chain) {
                         if (!launch_encode_pipe3(m, ea, wpc, st)) {
                             ctx->err = "no chain kernel instantiation for this model";
@@ -978,8 +978,10 @@ int zpaqgpu_init(zpaqgpu_ctx **out, int device) {
     if (const char *v = std::getenv("ZPAQGPU_SPEC_PROBE")) ctx->spec_probe = std::atoi(v) != 0;
     if (const char *v = std::getenv("ZPAQGPU_PULL")) ctx->pull_how = std::atoi(v) & 3;
     if (const char *v = std::getenv("ZPAQGPU_GUESS")) ctx->guess = std::max(0, std::min(4, std::atoi(v)));
-    if (const char *v = std::getenv("ZPAQGPU_ENC_FLAGS")) ctx->enc_l1_pull = std::atoi(v) != 0;
+    if (const char *v = std::getenv("ZPAQGPU_ENC_FLAGS")) ctx->enc_flags = std::atoi(v) & 3;
     if (const char *v = std::getenv("ZPAQGPU_GENERIC")) ctx->generic_warp = std::strcmp(v, "lane0") != 0;
+    if (const char *v = std::getenv("ZPAQGPU_WS_LIMIT_MB")) ctx->ws_limit = u64(std::atoll(v)) << 20;  // profiling: ncu saves
+    // and restores every device buffer between replay passes
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->sm_count = prop.multiProcessorCount;
     bool ok = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) == cudaSuccess &&

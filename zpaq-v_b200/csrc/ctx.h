@@ -45,7 +45,8 @@ struct zpaqgpu_ctx {
     void *tables_mem = nullptr;
     int kernel_pref = ZPAQGPU_KERNEL_AUTO;
     int table_mode = ZPAQGPU_TABLES_AUTO;
-    bool enc_l1_pull = true;   // ZPAQGPU_ENC_FLAGS=0: the encoder's history warp does not pull the next slot line into L1
+    int enc_flags = 1;         // ZPAQGPU_ENC_FLAGS: 0 no L1 pull in the encoder's history warp, 1 pull the next nibble's slot
+                               // line (default), 3 pull the line of the nibble after next (two nibbles of lead)
     int pull_how = 0;          // ZPAQGPU_PULL: how (experiments)
     int guess = 1;             // ZPAQGPU_GUESS=n: the two-warp decoder pulls the n (0, 1, 2, 4) likeliest next slot lines a nibble early
     bool generic_warp = true;  // ZPAQGPU_GENERIC=lane0: the one-lane generic kernels also for headers the warp kernel takes (A/B)
