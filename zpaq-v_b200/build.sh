@@ -34,5 +34,5 @@ OBJS="build/model.o"
 for f in $CU; do
   [ -f csrc/$f.cu ] && OBJS="$OBJS build/$f.o"
 done
-$NVCC -shared -cudart static -gencode arch=compute_100a,code=sm_100a -o libzpaqgpu.so $OBJS
+$NVCC -shared -cudart static -gencode arch=compute_100a,code=sm_100a -o libzpaqgpu.so $OBJS -ldl
 echo "built $(pwd)/libzpaqgpu.so"

@@ -220,6 +220,7 @@ float elapsed(cudaEvent_t a, cudaEvent_t b) {
 // Compression job: blocks of segments, plaintext already on the device.
 // ------------------------------------------------------------------------------------------
 int run_compress(zpaqgpu_ctx *ctx, CompressJob &job) {
+    Range nvtx_job("zpaqgpu:compress_job");
     const Model &m = *job.model;
     const int n_blocks = int(job.blocks.size()), n_segs = int(job.segs.size());
     ctx->stats = zpaqgpu_stats{};
@@ -345,6 +346,7 @@ int run_compress(zpaqgpu_ctx *ctx, CompressJob &job) {
                 bool overflow = false;
                 for (int first = 0; first < n_blocks && !overflow; first += tp.slots) {
                     const int n = std::min(tp.slots, n_blocks - first);
+                    Range nvtx_wave("zpaqgpu:encode_wave");
                     CK(cudaEventRecord(ctx->ev[0], st));
                     ModelDev md;
                     if ((rc = prepare_wave(ctx, mod, tp, n, md))) return rc;
@@ -438,6 +440,7 @@ std::string size_comment(u64 n) { return std::to_string(n) + " bytes"; }
 // compression job, without the copy back.  *total receives the archive size.
 int compress_stage(zpaqgpu_ctx *ctx, const Model &m, const uint8_t *in, const uint64_t *in_off, int n_blocks,
                    const char *const *names, const char *const *comments, u64 *total) {
+    Range nvtx_call("zpaqgpu:compress_stage");
     CK(cudaSetDevice(ctx->device));
     const u64 base = in_off[0], total_in = in_off[n_blocks] - base;
     if (total_in > 0 && !in) return ZPAQGPU_E_ARG;
@@ -484,6 +487,7 @@ int compress_stage(zpaqgpu_ctx *ctx, const Model &m, const uint8_t *in, const ui
 
 // The staged archive back to the host: `total` bytes to out, the n_blocks+1 offsets (plus `shift`) to out_off.
 int compress_fetch(zpaqgpu_ctx *ctx, int n_blocks, u64 total, uint8_t *out, uint64_t *out_off, u64 shift) {
+    Range nvtx_call("zpaqgpu:compress_fetch");
     CK(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
     CK(cudaMemcpyAsync(out_off, ctx->out_off.p, 8 * size_t(n_blocks + 1), cudaMemcpyDeviceToHost, st));
@@ -543,6 +547,7 @@ struct DecompressJob {
 };
 
 int run_decompress(zpaqgpu_ctx *ctx, DecompressJob &job, bool caller_owns_plain) {
+    Range nvtx_job("zpaqgpu:decompress_job");
     cudaStream_t st = ctx->stream;
     const int n = int(job.cand.size());
     ctx->stats = zpaqgpu_stats{};
@@ -628,6 +633,7 @@ int run_decompress(zpaqgpu_ctx *ctx, DecompressJob &job, bool caller_owns_plain)
                         bool overflow = false;
                         for (int first = i; first < j && !overflow; first += tp.slots) {
                             const int cnt = std::min(tp.slots, j - first);
+                            Range nvtx_wave("zpaqgpu:decode_wave");
                             DecodeArgs da;
                             da.tables = ctx->tables;
                             da.workspace = static_cast<u8 *>(ctx->workspace.p);
@@ -787,6 +793,7 @@ u64 comment_hint(const uint8_t *arc, u64 len, u64 payload) {
 int decode_archive_dev(zpaqgpu_ctx *ctx, const uint8_t *arc, u64 len, std::vector<DecodedSeg> &segs,
                        const u8 **d_plain, int *status_out, u64 *total_out) {
     segs.clear();
+    Range nvtx_call("zpaqgpu:decode_archive");
     CK(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
     int rc;

@@ -1,6 +1,8 @@
 // ctx.h -- internals of libzpaqgpu shared by api.cu and jidac.cu: the context, grow-only device
 // buffers and the compression job that both the block API and the jidac front end submit.
 #pragma once
+#include <nvtx3/nvToolsExt.h>
+
 #include <exception>
 #include <new>
 #include <string>
@@ -92,6 +94,14 @@ struct zpaqgpu_ctx {
     } while (0)
 
 namespace zg {
+
+// NVTX range around a stage of a call (tracing): visible in nsys / ncu --nvtx, free otherwise.
+struct Range {
+    explicit Range(const char *name) { nvtxRangePushA(name); }
+    ~Range() { nvtxRangePop(); }
+    Range(const Range &) = delete;
+    Range &operator=(const Range &) = delete;
+};
 
 // Nothing may leave the C ABI as a C++ exception: host allocation failures and the like become status codes.
 template <class R, class F>

@@ -310,6 +310,7 @@ struct Timer {
 
 int jidac_front(zpaqgpu_ctx *ctx, const uint8_t *in, const uint64_t *in_off, int n_files, int fragment, int dedup,
                 bool gather, Front &R) {
+    Range nvtx_front("zpaqgpu:jidac_front");
     zpaqgpu_jidac_stats &S = ctx->jd_stats;
     S = zpaqgpu_jidac_stats{};
     S.n_files = n_files;

@@ -41,8 +41,6 @@ __host__ __device__ constexpr size_t warp_smem_bytes(int ni, bool mix2) {
 }
 constexpr size_t kSharedTables = 32768 * 2 + 4096 * 2 + 512;
 
-__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
-
 __device__ __forceinline__ uint4 ldg128(const u8 *p) {
     uint4 v;
     asm volatile("ld.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
@@ -172,30 +170,6 @@ struct ProbeBase {
             mix_h = mixv;
             stage_mix();
         }
-        // Paged tables put a page-table read in front of every slot probe.  The 16 possible slots of this
-        // byte's LOW nibble (keys h + 16 * (16..31)) are 256 bytes apart, one page each: their 16 table
-        // entries are consecutive words.  Pull them towards the SM now, a nibble before they are read.
-        if (md->paged && powner && pcand == 0u && spec) {
-            const u32 first = (((h + 256u) * 16u) & (ht_len - 16u)) / kPageBytes;
-            const u32 *pt = reinterpret_cast<const u32 *>(ht);
-            prefetch_l2(pt + first);
-            prefetch_l2(pt + ((first + 15u) & (max(ht_len / kPageBytes, 1u) - 1u)));
-        }
-    }
-
-    // Paged tables, start of the low nibble (high nibble `hi` decoded): the next byte is one of 16, so the
-    // page-table entry of its high-nibble slot is one of 16 per component.  Lane (pc, pcand) asks L2 for the
-    // entries of bytes 16 * hi + 4 * pcand .. + 3; the probe two bits later then finds its entry there
-    // instead of in HBM.
-    __device__ __forceinline__ void pte_ahead(u32 hi) {
-        if (!(md->paged && powner && spec)) return;
-        const u32 *pt = reinterpret_cast<const u32 *>(ht);
-#pragma unroll
-        for (u32 k = 0; k < 4; ++k) {
-            u32 nh, mixv;
-            const u32 key = ctx_next(hi * 16u + pcand * 4u + k, pc, nh, mixv) + 16u;
-            prefetch_l2(pt + ((key * 16u) & (ht_len - 16u)) / kPageBytes);
-        }
     }
 
     // Address of a slot without side effects: nullptr when a paged table has no page there yet.
@@ -213,15 +187,6 @@ struct ProbeBase {
     // not requested (it changes at the write-back), nor an unmapped page.
     __device__ __forceinline__ void probe_issue(u32 c8part) {
         q_ok = false;
-        if (MIX2 && spec && ((c8part << 2) >= 256u)) {
-            // the MIX2 weights of the next byte are a 512-byte window that starts at its context hash: ask L2
-            // for the windows of the four possible bytes (lane = candidate x 64-byte line), so that stage_mix
-            // at the byte boundary does not wait for HBM
-            u32 nh, mixv;
-            ctx_next(((c8part << 2) | pcand) & 255u, pc, nh, mixv);
-            prefetch_l2(a16 + ((mixv + u32(pc) * 32u) & a16_mask));
-            if (pc == 7) prefetch_l2(a16 + ((mixv + 256u) & a16_mask));
-        }
         if (powner && spec) {
             const u32 c8new = (c8part << 2) | pcand;
             if (c8new < 256u) {
@@ -726,7 +691,6 @@ __global__ void __launch_bounds__(256, 1) k_decode_chain(DecodeArgs A) {
 #pragma unroll 1
             for (int half = 0; half < 2; ++half) {
                 C.probe(c8);
-                if (half == 1) C.pte_ahead(c8 & 15u);
                 if constexpr (TREE) decode_nibble_tree<NI, MIX2>(C, c8, low, high, code, io);
                 else code_nibble<NI, MIX2, true>(C, 0, c8, low, high, code, io);
             }

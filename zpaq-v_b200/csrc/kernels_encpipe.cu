@@ -147,8 +147,7 @@ __global__ void __launch_bounds__(672, 1) k_encode_pipe3(EncodeArgs A, int block
     u32 ht_len = 16;
     int sizebits = 0;
     uint4 sl = make_uint4(0, 0, 0, 0);
-    u32 pre_a = 0, pre_b = 0, pre_c = 0, pre_d = 0, sink_h = 0;
-    u32 pte_a = 0, pte_b = 0;  // paged tables: page-table entries of the next byte's two slots
+    u32 pre_a = 0, pre_b = 0, sink_h = 0;
     // C
     u16 *a16 = nullptr;
     u32 a16_mask = 0, mix_sel = 0;
@@ -245,33 +244,6 @@ __global__ void __launch_bounds__(672, 1) k_encode_pipe3(EncodeArgs A, int block
                             prefetch_l2(ht + (((k0 * 16u) & (ht_len - 16u)) & ~63u));
                             prefetch_l2(ht + (((k1 * 16u) & (ht_len - 16u)) & ~63u));
                         }
-                        // Paged tables put a page-table read in front of every probe: two HBM round trips per
-                        // nibble, one after the other.  The encoder knows every future context, so both are
-                        // taken off the path: the entries of byte vb+2 are asked into L2 now; the entries of
-                        // byte vb+1 (asked for a byte ago) are read into registers now and, one nibble later,
-                        // tell which slot lines to ask for.
-                        if (owner && M.paged) {
-                            const u32 *pt = reinterpret_cast<const u32 *>(ht);
-                            if (vb + 2 < total) {
-                                const u32 c2 = vbyte(vb + 2);
-                                const u32 k0 = h2 + 16u, k1 = h2 + 16u * (16u | (c2 >> 4));
-                                prefetch_l2(pt + ((k0 * 16u) & (ht_len - 16u)) / kPageBytes);
-                                prefetch_l2(pt + ((k1 * 16u) & (ht_len - 16u)) / kPageBytes);
-                            }
-                            pte_a = pte_b = 0;
-                            if (vb + 1 < total) {
-                                const u32 c1 = vbyte(vb + 1);
-                                const u32 k0 = h1 + 16u, k1 = h1 + 16u * (16u | (c1 >> 4));
-                                pte_a = pt[((k0 * 16u) & (ht_len - 16u)) / kPageBytes];
-                                pte_b = pt[((k1 * 16u) & (ht_len - 16u)) / kPageBytes];
-                            }
-                        }
-                    } else if (owner && M.paged && vb + 1 < total) {
-                        const u32 c1 = vbyte(vb + 1);
-                        const u32 o0 = ((h1 + 16u) * 16u) & (ht_len - 16u);
-                        const u32 o1 = ((h1 + 16u * (16u | (c1 >> 4))) * 16u) & (ht_len - 16u);
-                        if (pte_a) prefetch_l2(M.pool + u64(pte_a - 1u) * kPageBytes + (o0 & (kPageBytes - 64u)));
-                        if (pte_b) prefetch_l2(M.pool + u64(pte_b - 1u) * kPageBytes + (o1 & (kPageBytes - 64u)));
                     }
                     const u32 c8 = half ? (16u | (c >> 4)) : 1u;
                     const u32 nib = half ? (c & 15u) : (c >> 4);
@@ -293,19 +265,7 @@ __global__ void __launch_bounds__(672, 1) k_encode_pipe3(EncodeArgs A, int block
                         // The line of the NEXT nibble is known already (the encoder knows every future
                         // context): pull both of its sectors into L1 with two 4-byte loads nobody waits
                         // for, unless it is this slot's own line, which is about to change.
-                        if ((A.flags & 2) && !M.paged) {
-                            // two nibbles of lead: the pulls issued a nibble ago stay in flight (pre_c/pre_d),
-                            // this step issues the line of nibble N+2 -- high nibble of the next byte (key
-                            // H(vb+1) + 16) or its low nibble (key H(vb+1) + 16 * (16 | hi(byte vb+1)))
-                            pre_a = pre_c, pre_b = pre_d;
-                            if (N + 2 < NN) {
-                                const u32 c1 = vbyte(vb + 1);
-                                const u32 key2 = half ? h1 + 16u * (16u | (c1 >> 4)) : h1 + 16u;
-                                const u8 *nl = ht + (((key2 * 16u) & (ht_len - 16u)) & ~63u);
-                                asm volatile("ld.global.ca.u32 %0, [%1];" : "=r"(pre_c) : "l"(nl));
-                                asm volatile("ld.global.ca.u32 %0, [%1];" : "=r"(pre_d) : "l"(nl + 32));
-                            }
-                        } else if (A.flags && !M.paged && N + 1 < NN) {
+                        if (A.flags && !M.paged && N + 1 < NN) {
                             const u32 key1 = half ? h_next + 16u : h + 16u * (16u | (c >> 4));
                             const u8 *nl = ht + (((key1 * 16u) & (ht_len - 16u)) & ~63u);
                             if (nl != reinterpret_cast<u8 *>(reinterpret_cast<uintptr_t>(b0) & ~uintptr_t(63))) {
@@ -414,11 +374,6 @@ __global__ void __launch_bounds__(672, 1) k_encode_pipe3(EncodeArgs A, int block
                             __syncwarp();
                             for (int k = lane; k < 256; k += 32) V.a16s[k] = a16[(mix_h + u32(k)) & a16_mask];
                             __syncwarp();
-                            // the window of the NEXT byte starts at the hash of this one: ask L2 for its nine
-                            // lines now, a whole byte before they are staged
-                            u32 nh;
-                            const u32 hn = cx.next(cz, Z, nh);
-                            if (lane < 9) prefetch_l2(a16 + ((hn + u32(lane) * 32u) & a16_mask));
                         }
                         // "not EOF" flag: encode(0, p=0) => low += 1 (encoder.v:108)
                         low = low + 1;
@@ -509,7 +464,7 @@ __global__ void __launch_bounds__(672, 1) k_encode_pipe3(EncodeArgs A, int block
             if (lane == 0) A.pay_len[blk.first_seg + s] = written + fill;
         }
     }
-    if (role == 0 && sink_h + pre_a + pre_b + pre_c + pre_d == 0x9E3779B9u && A.n_blocks < 0) A.pay_len[0] = 0;  // keeps the pulls alive
+    if (role == 0 && sink_h + pre_a + pre_b == 0x9E3779B9u && A.n_blocks < 0) A.pay_len[0] = 0;  // keeps the pulls alive
 }
 
 // ------------------------------------------------------------------------------------------
