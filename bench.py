@@ -640,48 +640,63 @@ def run_per_level(args, E):
     return out
 
 
+GENERIC_HEADERS = {
+    # tests/test_oracle_kats.py CUSTOM_HEADERS: five components of five different types (nothing for the lanes
+    # to share) and twenty components with eight ICMs and four ISSEs (lanes of one type run together)
+    "icm_match_mix2_sse": [3, 10, 0, 0, 5, 3, 14, 4, 12, 14, 6, 10, 0, 1, 20, 255, 8, 12, 2, 9, 10, 3, 32, 100, 0,
+                           104, 17, 28, 59, 112, 25, 60, 25, 59, 112, 25, 65, 112, 25, 112, 56, 0],
+    "twenty": ([5, 10, 0, 0, 20] + [3, 10, 3, 11, 3, 12, 3, 10, 3, 11, 3, 12, 3, 10, 3, 11]
+               + [8, 11, 0, 8, 11, 8, 8, 10, 9, 8, 10, 3] + [4, 12, 14] + [2, 12, 20, 2, 14, 255] + [5, 10, 11, 128]
+               + [9, 8, 15, 16, 64] + [7, 8, 0, 17, 20, 255] + [6, 10, 16, 17, 24, 255] + [9, 10, 18, 32, 255] + [0]
+               + [96, 4, 28] + [59, 112, 25, 10] * 6 + [59, 112, 25] * 8 + [60, 25] * 3 + [59, 112, 25] * 3 + [56, 0]),
+}
+
+
 def run_generic(args, E):
-    """a header outside the -m1..-m5 shape (ICM, MATCH, MIX2, ISSE, SSE + a HASH/HASHD program)
-    through the generic path: the warp kernel (component per lane, warp-uniform ZPAQL) beside the one-lane
-    kernel it replaces (ZPAQGPU_GENERIC=lane0), same blocks, kernel time from CUDA events."""
-    datagen, z = E["datagen"], E["z"]
+    """headers outside the -m1..-m5 shape through the generic path: the warp kernel (component
+    per lane, warp-uniform ZPAQL) beside the one-lane kernel it replaces (ZPAQGPU_GENERIC=lane0), same blocks,
+    kernel time from CUDA events."""
+    z = E["z"]
     import oracle_binding as ob
-    hdr = bytes([3, 10, 0, 0, 5, 3, 14, 4, 12, 14, 6, 10, 0, 1, 20, 255, 8, 12, 2, 9, 10, 3, 32, 100, 0,
-                 104, 17, 28, 59, 112, 25, 60, 25, 59, 112, 25, 65, 112, 25, 112, 56, 0])
     nb, bb = 592, 32768
     text = E["text"]
     blocks = [text[k * bb:(k + 1) * bb].tobytes() for k in range(nb)]
-    res = {"what": "custom header icm_match_mix2_sse (5 components, 16-op HCOMP), %d x %d KiB text blocks, host "
-                   "buffers" % (nb, bb // 1024), "blocks": nb, "block_bytes": bb}
-    arcs = {}
-    for name, env in (("warp", None), ("lane0", "lane0")):
-        if env:
-            os.environ["ZPAQGPU_GENERIC"] = env
-        else:
-            os.environ.pop("ZPAQGPU_GENERIC", None)
-        ctx = z.Context(E["dev"].index)
-        try:
-            ctx.compress_blocks(0, blocks[:8], header=hdr)
-            got = ctx.compress_blocks(0, blocks, header=hdr)
-            st_c = ctx.stats()
-            plain, segs, status = ctx.decompress_archive(b"".join(got))
-            st_d = ctx.stats()
-            if status != 0 or plain != b"".join(blocks):
-                raise SystemExit("generic %s: round trip mismatch" % name)
-            arcs[name] = got
-            res[name] = {"compress_kernel_ms": round(st_c["codec_ms"], 2), "decompress_kernel_ms": round(st_d["codec_ms"], 2),
-                         "compress_kernel_mb_s": round(nb * bb / st_c["codec_ms"] / 1e3, 2),
-                         "decompress_kernel_mb_s": round(nb * bb / st_d["codec_ms"] / 1e3, 2), "kernel": st_c["kernel"]}
-        finally:
-            ctx.close()
-    os.environ.pop("ZPAQGPU_GENERIC", None)
-    res["speedup_over_lane0"] = {"compress": round(res["lane0"]["compress_kernel_ms"] / res["warp"]["compress_kernel_ms"], 2),
-                                 "decompress": round(res["lane0"]["decompress_kernel_ms"] / res["warp"]["decompress_kernel_ms"], 2)}
-    idx = [0, 77, 300, 591]
-    res["byte_identical_to_oracle"] = all(arcs["warp"][k] == arcs["lane0"][k] == ob.compress_block(0, blocks[k], "", "", header=hdr)
-                                          for k in idx)
-    res["parity_blocks"] = idx
-    return res
+    out = {"what": "custom headers through the generic kernels, %d x %d KiB text blocks, host buffers; warp = "
+                   "kernels_genwarp.cu, lane0 = the one-lane kernel" % (nb, bb // 1024), "blocks": nb, "block_bytes": bb}
+    for hname, hbytes in GENERIC_HEADERS.items():
+        hdr = bytes(hbytes)
+        res, arcs = {}, {}
+        for name, env in (("warp", None), ("lane0", "lane0")):
+            if env:
+                os.environ["ZPAQGPU_GENERIC"] = env
+            else:
+                os.environ.pop("ZPAQGPU_GENERIC", None)
+            ctx = z.Context(E["dev"].index)
+            try:
+                ctx.compress_blocks(0, blocks[:8], header=hdr)
+                got = ctx.compress_blocks(0, blocks, header=hdr)
+                st_c = ctx.stats()
+                plain, segs, status = ctx.decompress_archive(b"".join(got))
+                st_d = ctx.stats()
+                if status != 0 or plain != b"".join(blocks):
+                    raise SystemExit("generic %s/%s: round trip mismatch" % (hname, name))
+                arcs[name] = got
+                res[name] = {"compress_kernel_ms": round(st_c["codec_ms"], 2), "decompress_kernel_ms": round(st_d["codec_ms"], 2),
+                             "compress_kernel_mb_s": round(nb * bb / st_c["codec_ms"] / 1e3, 2),
+                             "decompress_kernel_mb_s": round(nb * bb / st_d["codec_ms"] / 1e3, 2)}
+            finally:
+                ctx.close()
+        os.environ.pop("ZPAQGPU_GENERIC", None)
+        res["speedup_over_lane0"] = {
+            "compress": round(res["lane0"]["compress_kernel_ms"] / res["warp"]["compress_kernel_ms"], 2),
+            "decompress": round(res["lane0"]["decompress_kernel_ms"] / res["warp"]["decompress_kernel_ms"], 2)}
+        idx = [0, 77, 300, 591]
+        res["byte_identical_to_oracle"] = all(
+            arcs["warp"][k] == arcs["lane0"][k] == ob.compress_block(0, blocks[k], "", "", header=hdr) for k in idx)
+        res["parity_blocks"] = idx
+        res["components"] = hbytes[4]
+        out[hname] = res
+    return out
 
 
 def run_jidac(args, E):
