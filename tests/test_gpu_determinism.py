@@ -1,0 +1,45 @@
+"""Race hunting without compute-sanitizer (the GPU pool refuses it: profiles/r02_sanitizer_refused.txt).
+
+The kernels that could hide a race are the ones whose warps exchange data: the three-warp encoder (named
+barrier + shared rings), the tree decoder (table updates handed down between lanes, shared stage and rings)
+and the paged tables (pages mapped by atomics from a pool shared by every block of the wave).  A race shows
+up as a result that depends on timing, so the same blocks are coded under different packings -- 1, 5 and 7
+blocks per CTA, one wave and several, dense and paged tables, twice each -- and every block of every run must
+equal the CPU oracle's bytes."""
+import pytest
+
+import datagen
+import oracle_binding as ob
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(autouse=True)
+def _reset(gpu_ctx):
+    yield
+    gpu_ctx.set_table_mode(0)
+    gpu_ctx.set_workspace_limit(0)
+
+
+def _blocks(n):
+    out = []
+    for k in range(n):
+        size = 1500 + (k * 397) % 2600
+        out.append(datagen.mixed_block(k, size, datagen.SEED0 + 500))
+    return out
+
+
+@pytest.mark.parametrize("level", [1, 2, 4])
+def test_same_bytes_under_every_packing(gpu_ctx, level):
+    blocks = _blocks(1040)
+    want = None
+    for n, mode, limit_gib in ((37, 0, 0), (600, 0, 0), (1040, 0, 0), (1040, 2, 0), (1040, 1, 2), (600, 2, 1)):
+        gpu_ctx.set_table_mode(mode)
+        gpu_ctx.set_workspace_limit(limit_gib << 30)
+        for rep in range(2):
+            got = gpu_ctx.compress_blocks(level, blocks[:n])
+            if want is None:
+                want = [ob.compress_block(level, b, "", "") for b in blocks]
+            assert got == want[:n], (level, n, mode, limit_gib, rep)
+            plain, segs, status = gpu_ctx.decompress_archive(b"".join(got))
+            assert status == 0 and plain == b"".join(blocks[:n]) and all(s["sha1_ok"] == 1 for s in segs), (level, n, mode)

@@ -11,13 +11,18 @@
 //    MIX2, SSE, MATCH) stay in the block's HBM workspace.
 //  * predict (predictor.v:536-668) runs in two parts.  FETCH: every lane does what does not depend on
 //    another component -- the hash-slot search of ICM/ISSE (find_ht, three candidates of one 64-byte line),
-//    the bit-history state, the table entry, the MIX2 weight, CONS/CM/ICM/MATCH predictions -- so the
-//    HBM/L2 round trips of all components overlap.  COMBINE: components that read other predictions
-//    (AVG/MIX2/MIX/ISSE/SSE) are evaluated level by level (level = 1 + deepest input in front of it, from
-//    the host); inputs travel by SHFL.  The reference evaluates in index order and lets a component read
-//    p[j] of a LATER component (it only checks j < n): that value is the one of the previous bit, kept
-//    here as `pp`.  A MIX is a warp dot product: lane j+l multiplies its own prediction with weight l, the
-//    sum is one __reduce_add_sync (wrapping 32-bit adds, order-free); its update is one weight per lane.
+//    the bit-history state, the table entry, the MIX2 weight, CONS/CM/ICM/MATCH predictions.  Lanes of one
+//    type run together; different types take different branches one after the other.  COMBINE: components
+//    that read other predictions (AVG/MIX2/MIX/ISSE/SSE) are evaluated level by level (level = 1 + deepest
+//    input in front of it, from the host); inputs travel by SHFL.  The reference evaluates in index order
+//    and lets a component read p[j] of a LATER component (it only checks j < n): that value is the one of
+//    the previous bit, kept here as `pp`.  A MIX is a warp dot product: lane j+l multiplies its own
+//    prediction with weight l, the sum is one __reduce_add_sync (wrapping 32-bit adds, order-free); its
+//    update is one weight per lane.
+//    Measured (ncu, profiles/r02_genwarp_decode_lines.txt): the kernel is bound by its instruction stream
+//    (3 300 warp instructions per nibble for a five-type header, 5 % waiting for memory), so what the lanes
+//    buy is one pass for all components of a type; issuing the loads of all types from one place first was
+//    tried and was slower (743 against 669 ms: more instructions, nothing to hide).
 //  * update (predictor.v:672-824) touches only a component's own tables and reads the finished p[]: all
 //    lanes at once.
 //  * the ZPAQL interpreter (zpaql.v:167-954) is WARP-UNIFORM: a, b, c, d, f, pc are replicated in every
@@ -35,9 +40,7 @@ namespace {
 
 constexpr unsigned kAll = 0xFFFFFFFFu;
 constexpr int kWarpsPerCta = 4;
-constexpr size_t kConstBytes = 32768 * 2 + 4096 * 2 + 512 + 1024 * 4 + 256 * 4;  // stretch_pad, squash_pad, next-state
-                                                                                 // pairs, dt (CM), dt2k (MATCH)
-constexpr size_t kHdrBytes = 1024;                           // per CTA: the model header (HCOMP program) when it fits
+constexpr size_t kConstBytes = 32768 * 2 + 4096 * 2 + 512;  // stretch_pad, squash_pad, next-state pairs
 constexpr size_t kVmBytes = 4096;                            // per warp: R (1 KiB) + H and M when they fit
 constexpr size_t kTabBytes = 24576;                          // per warp: ICM / ISSE adaptive tables
 constexpr size_t kWarpBytes = kVmBytes + kTabBytes;
@@ -247,7 +250,7 @@ struct GenW {
         stretch_pad = reinterpret_cast<const int16_t *>(smem_const);
         squash_pad = reinterpret_cast<const u16 *>(smem_const + 65536);
         nex = smem_const + 65536 + 8192;
-        dt = reinterpret_cast<const i32 *>(smem_const + 65536 + 8192 + 512), dt2k = dt + 1024;
+        dt = T.dt, dt2k = T.dt2k;
         type = C_NONE, a = b = c = limit = 0, cxt = 0, h = 0, p = pp = 0, lvl = 0;
         cm = nullptr, ht = nullptr, a16 = nullptr, cm_len = ht_len = 1, q0 = q1 = q2 = q3 = 0;
         ja = jb = 0, va = vb = false, e0 = e1 = 0;
@@ -299,7 +302,7 @@ struct GenW {
         vm.a = vm.b = vm.c = vm.d = 0, vm.f = 0, vm.pc = M.hbegin;
         vm.has_m = M.m_len != 0, vm.has_h = M.h_len != 0;
         vm.m_mask = M.m_len - 1, vm.h_mask = M.h_len - 1;
-        vm.hdr = M.header_len <= i32(kHdrBytes) ? smem_const + kConstBytes : M.header, vm.hbegin = M.hbegin, vm.hend = M.hend, vm.hdr_len = M.header_len;
+        vm.hdr = M.header, vm.hbegin = M.hbegin, vm.hend = M.hend, vm.hdr_len = M.header_len;
         vm.r = reinterpret_cast<u32 *>(smem_vm);
         const size_t hm_bytes = size_t(M.h_len) * 4 + M.m_len;
         if (hm_bytes <= kVmBytes - 1024) {
@@ -360,73 +363,45 @@ struct GenW {
     __device__ i32 predict() {  // predictor.v:536-668; returns squash(p[n-1])
         pp = p;
         // ---- FETCH: everything that needs no other component ----
-        // Lanes of different component types take different branches, and a branch that waits for a load
-        // keeps the whole warp waiting.  So the branches only compute ADDRESSES; the loads themselves are
-        // issued from one place for all lanes (phase 2) and the HBM/L2 round trips of all components overlap.
-        const bool nibble = c8 == 1 || (c8 & 0xf0) == 16;
-        // phase 0: find_ht of the ICM and ISSE lanes (one code path for both)
-        if (act && nibble && (type == C_ICM || type == C_ISSE)) probe(a + 2, h + 16u * c8);
-        // phase 1: addresses
-        const u32 *ld0 = nullptr;
-        bool two = false;
-        u32 sh0 = 0;
         if (act) {
-            switch (type) {
-            case C_CM:
-                cxt = h ^ hmap4;
-                ld0 = cm + (cxt & (cm_len - 1));
-                break;
-            case C_ICM:
-                cxt = slot_state(hmap4 & 15u);
-                ld0 = cm + cxt;
-                break;
-            case C_MATCH:
-                if (a != 0) {
-                    const u32 idx = u32(limit - b) & (ht_len - 1);
-                    ld0 = reinterpret_cast<const u32 *>(ht + (idx & ~3u));
-                    sh0 = (idx & 3u) * 8u;
-                }
-                break;
-            case C_MIX2:
-                cxt = (h + (c8 & q3)) & u32(c - 1);
-                ld0 = reinterpret_cast<const u32 *>(a16 + (cxt & ~1u));
-                sh0 = (cxt & 1u) * 16u;
-                break;
-            case C_MIX:
-                cxt = u32((i32(h) + (i32(c8) & i32(q1))) & (c - 1));
-                break;
-            case C_ISSE:
-                cxt = slot_state(hmap4 & 15u);
-                ld0 = cm + cxt * 2;
-                two = true;
-                break;
-            case C_SSE: cxt = (h + c8) * 32u; break;
-            default: break;
-            }
-        }
-        // phase 2: the loads, all lanes at once
-        const u32 x0 = ld0 ? ld0[0] : 0u;
-        const u32 x1 = two ? ld0[1] : 0u;
-        // phase 3: predictions of the components that need nobody else
-        if (act) {
+            const bool nibble = c8 == 1 || (c8 & 0xf0) == 16;
             switch (type) {
             case C_CONS: p = (a - 128) * 16; break;
             case C_CM:
-                e0 = i32(x0);
-                p = stretch(i32(x0 >> 17));
+                cxt = h ^ hmap4;
+                e0 = i32(cm[cxt & (cm_len - 1)]);
+                p = stretch(i32(u32(e0) >> 17));
                 break;
-            case C_ICM: p = stretch(i32(x0 >> 8)); break;
+            case C_ICM:
+                if (nibble) probe(a + 2, h + 16u * c8);
+                cxt = slot_state(hmap4 & 15u);
+                p = stretch(i32(cm[cxt] >> 8));
+                break;
             case C_MATCH:
                 if (a == 0) {
                     p = 0;
                 } else {
-                    c = i32((((x0 >> sh0) & 255u) >> (7 - i32(cxt))) & 1u);
+                    const i32 idx = (limit - b) & i32(ht_len - 1);
+                    c = i32((u32(ht[idx]) >> (7 - i32(cxt))) & 1u);
                     p = stretch((dt2k[a & 255] * (c * -2 + 1)) & 32767);
                 }
                 break;
-            case C_MIX2: e0 = i32((x0 >> sh0) & 0xFFFFu); break;
-            case C_ISSE: e0 = i32(x0), e1 = i32(x1); break;
-            case C_MIX: case C_SSE: case C_AVG: break;
+            case C_MIX2:
+                cxt = (h + (c8 & q3)) & u32(c - 1);
+                e0 = a16[cxt];
+                break;
+            case C_MIX:
+                cxt = u32((i32(h) + (i32(c8) & i32(q1))) & (c - 1));
+                break;
+            case C_ISSE: {
+                if (nibble) probe(a + 2, h + 16u * c8);
+                cxt = slot_state(hmap4 & 15u);
+                const uint2 w = *reinterpret_cast<const uint2 *>(cm + cxt * 2);
+                e0 = i32(w.x), e1 = i32(w.y);
+                break;
+            }
+            case C_SSE: cxt = (h + c8) * 32u; break;
+            case C_AVG: break;
             default: p = 0; break;
             }
         }
@@ -434,34 +409,29 @@ struct GenW {
         for (i32 lv = 1; lv < n_levels; ++lv) {
             const i32 pj = input(ja), pk = input(jb);
             const bool now = act && lvl == lv;
-            // SSE reads two neighbouring cells chosen by its input: address first, loads from one place
-            i32 sse_wt = 0;
-            const u32 *lds = nullptr;
-            if (now && type == C_SSE) {
-                i32 pq = va ? pj + 992 : 992;
-                pq = max(0, min(1983, pq));
-                sse_wt = pq & 63;
-                pq >>= 6;
-                const i32 idx = i32(cxt) + pq;
-                sse_ok = idx >= 0 && idx + 1 < i32(cm_len);
-                if (sse_ok) lds = cm + idx;
-                cxt = u32(idx) + u32(sse_wt >> 5);
-                sse_hi = (sse_wt >> 5) != 0;
-            }
-            const u32 y0 = lds ? lds[0] : 0u, y1 = lds ? lds[1] : 0u;
             if (now) {
                 switch (type) {
                 case C_AVG: p = (va && vb) ? ((pj * c + pk * (256 - c)) >> 8) : 0; break;
                 case C_MIX2: p = (va && vb) ? d_clamp2k((e0 * pj + (65536 - e0) * pk) >> 16) : 0; break;
                 case C_ISSE: p = va ? d_clamp2k((e0 * pj + e1 * 64) >> 16) : d_clamp2k(e1 >> 10); break;
-                case C_SSE:
+                case C_SSE: {
+                    i32 pq = va ? pj + 992 : 992;
+                    pq = max(0, min(1983, pq));
+                    const i32 wt = pq & 63;
+                    pq >>= 6;
+                    const i32 idx = i32(cxt) + pq;
+                    sse_ok = idx >= 0 && idx + 1 < i32(cm_len);
                     if (sse_ok) {
-                        e0 = i32(y0), e1 = i32(y1);
-                        p = stretch((i32(y0 >> 10) * (64 - sse_wt) + i32(y1 >> 10) * sse_wt) >> 13);
+                        e0 = i32(cm[idx]), e1 = i32(cm[idx + 1]);
+                        const i32 p1 = i32(u32(e0) >> 10), p2 = i32(u32(e1) >> 10);
+                        p = stretch((p1 * (64 - wt) + p2 * wt) >> 13);
                     } else {
                         p = 0;
                     }
+                    cxt = u32(idx) + u32(wt >> 5);
+                    sse_hi = (wt >> 5) != 0;
                     break;
+                }
                 default: break;
                 }
             }
@@ -594,9 +564,7 @@ struct GenW {
     }
 };
 
-__device__ __forceinline__ void load_const_tables(u8 *smem, const DevTables &T, const ModelDev &M) {
-    if (M.header_len <= i32(kHdrBytes))
-        for (int k = threadIdx.x; k < M.header_len; k += blockDim.x) smem[kConstBytes + k] = M.header[k];
+__device__ __forceinline__ void load_const_tables(u8 *smem, const DevTables &T) {
     const uint4 *g = reinterpret_cast<const uint4 *>(T.stretch_pad);
     uint4 *d = reinterpret_cast<uint4 *>(smem);
     for (int k = threadIdx.x; k < 4096; k += blockDim.x) d[k] = g[k];
@@ -605,8 +573,6 @@ __device__ __forceinline__ void load_const_tables(u8 *smem, const DevTables &T, 
     for (int k = threadIdx.x; k < 512; k += blockDim.x) d2[k] = g2[k];
     u8 *s_nex = smem + 65536 + 8192;
     for (int k = threadIdx.x; k < 512; k += blockDim.x) s_nex[k] = T.nex[k];
-    i32 *s_dt = reinterpret_cast<i32 *>(smem + 65536 + 8192 + 512);
-    for (int k = threadIdx.x; k < 1024 + 256; k += blockDim.x) s_dt[k] = T.dt[k];  // dt2k follows dt in the table image
     __syncthreads();
 }
 
@@ -658,13 +624,13 @@ __device__ __forceinline__ i32 dec_bit(u32 &low, u32 &high, u32 &code, u32 p16, 
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kWarpsPerCta * 32) k_encode_genwarp(EncodeArgs A) {
     extern __shared__ __align__(16) u8 smem[];
-    load_const_tables(smem, A.tables, A.model);
+    load_const_tables(smem, A.tables);
     const int wic = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int warp = blockIdx.x * kWarpsPerCta + wic;
     if (warp >= A.n_blocks) return;
     GenW g;
     g.block_init(A.model, A.workspace + u64(warp) * A.model.ws_bytes, A.tables, smem,
-                 smem + kConstBytes + kHdrBytes + size_t(wic) * kWarpBytes);
+                 smem + kConstBytes + size_t(wic) * kWarpBytes);
     const EncBlock blk = A.blocks[A.order[A.first_block + warp]];
     for (u32 s = 0; s < blk.n_seg; ++s) {
         const EncSeg seg = A.segs[blk.first_seg + s];
@@ -696,14 +662,14 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) k_encode_genwarp(EncodeArgs
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kWarpsPerCta * 32) k_decode_genwarp(DecodeArgs A) {
     extern __shared__ __align__(16) u8 smem[];
-    load_const_tables(smem, A.tables, A.model);
+    load_const_tables(smem, A.tables);
     const int wic = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int warp = blockIdx.x * kWarpsPerCta + wic;
     if (warp >= A.n_blocks) return;
     const int bi = int(A.order[A.first_block + warp]);
     GenW g;
     g.block_init(A.model, A.workspace + u64(warp) * A.model.ws_bytes, A.tables, smem,
-                 smem + kConstBytes + kHdrBytes + size_t(wic) * kWarpBytes);
+                 smem + kConstBytes + size_t(wic) * kWarpBytes);
     const DecBlock blk = A.blocks[bi];
     SourceW in{A.arc, blk.arc_pos, A.arc_len};
     DecBlockOut res;
@@ -792,7 +758,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) k_decode_genwarp(DecodeArgs
 // ------------------------------------------------------------------------------------------
 bool genwarp_supports(const Model &m) { return m.n >= 1 && m.n <= 32; }
 
-static size_t genwarp_smem() { return kConstBytes + kHdrBytes + size_t(kWarpsPerCta) * kWarpBytes; }
+static size_t genwarp_smem() { return kConstBytes + size_t(kWarpsPerCta) * kWarpBytes; }
 
 bool launch_encode_genwarp(const EncodeArgs &A, cudaStream_t s) {
     if (cudaFuncSetAttribute(k_encode_genwarp, cudaFuncAttributeMaxDynamicSharedMemorySize, int(genwarp_smem())) !=
