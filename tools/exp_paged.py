@@ -19,7 +19,7 @@ def main():
     ap.add_argument("--level", type=int, default=4)
     ap.add_argument("--blocks", type=int, default=256)
     ap.add_argument("--block-kib", type=int, default=1024)
-    ap.add_argument("--limits-gib", default="0,32,8")
+    ap.add_argument("--limits-gib", default="0")
     args = ap.parse_args()
     import datagen
     import zpaq_v_b200 as z
@@ -28,12 +28,15 @@ def main():
     blocks = [data[i * bb:(i + 1) * bb].tobytes() for i in range(nb)]
     want = data[:nb * bb].tobytes()
     first = None
-    runs = [("dense", 1, 0)] + [("paged", 2, int(g)) for g in args.limits_gib.split(",")]
-    for name, mode, gib in runs:
+    runs = [("dense", 1, 0, "1")]
+    for g in args.limits_gib.split(","):
+        runs += [("paged", 2, int(g), "1"), ("paged", 2, int(g), "0")]
+    for name, mode, gib, ahead in runs:
+        os.environ["ZPAQGPU_AHEAD"] = ahead  # read when the context is created
         ctx = z.Context(0)
         ctx.set_table_mode(mode)
         ctx.set_workspace_limit(gib << 30)
-        res = {"level": args.level, "blocks": nb, "block_kib": args.block_kib, "tables": name, "ws_limit_gib": gib}
+        res = {"level": args.level, "blocks": nb, "block_kib": args.block_kib, "tables": name, "ws_limit_gib": gib, "ahead": int(ahead)}
         try:
             for rep in range(2):
                 arc = ctx.compress_blocks(args.level, blocks)

@@ -357,7 +357,7 @@ int run_compress(zpaqgpu_ctx *ctx, CompressJob &job) {
                     ea.in = job.d_in, ea.arena = static_cast<u8 *>(ctx->arena.p);
                     ea.blocks = d_blocks, ea.segs = d_esegs, ea.pay_len = static_cast<u64 *>(ctx->pay_len.p);
                     ea.order = d_order, ea.first_block = first, ea.n_blocks = n;
-                    ea.flags = ctx->enc_flags;
+                    ea.flags = (ctx->enc_flags & 1) | (ctx->ahead ? 0 : 4);
                     if (chain) {
                         if (!launch_encode_pipe3(m, ea, wpc, st)) {
                             ctx->err = "no chain kernel instantiation for this model";
@@ -644,7 +644,7 @@ int run_decompress(zpaqgpu_ctx *ctx, DecompressJob &job, bool caller_owns_plain)
                             da.seg_count = static_cast<u32 *>(ctx->misc.p);
                             da.seg_cap = seg_cap, da.first_block = first, da.n_blocks = cnt;
                             da.order = reinterpret_cast<const u32 *>(static_cast<const u8 *>(ctx->desc.p) + o_dorder);
-                            da.flags = (ctx->spec_probe ? 1 : 0) | (ctx->guess << 8) | (ctx->pull_how << 12);
+                            da.flags = (ctx->spec_probe ? 1 : 0) | (ctx->ahead ? 0 : 2) | (ctx->guess << 8) | (ctx->pull_how << 12);
                             CK(cudaEventRecord(ctx->ev[0], st));
                             if (store) {
                                 da.model = mod.dense;
@@ -986,6 +986,7 @@ int zpaqgpu_init(zpaqgpu_ctx **out, int device) {
     if (const char *v = std::getenv("ZPAQGPU_PULL")) ctx->pull_how = std::atoi(v) & 3;
     if (const char *v = std::getenv("ZPAQGPU_GUESS")) ctx->guess = std::max(0, std::min(4, std::atoi(v)));
     if (const char *v = std::getenv("ZPAQGPU_ENC_FLAGS")) ctx->enc_flags = std::atoi(v) & 3;
+    if (const char *v = std::getenv("ZPAQGPU_AHEAD")) ctx->ahead = std::atoi(v) != 0;
     if (const char *v = std::getenv("ZPAQGPU_GENERIC")) ctx->generic_warp = std::strcmp(v, "lane0") != 0;
     if (const char *v = std::getenv("ZPAQGPU_WS_LIMIT_MB")) ctx->ws_limit = u64(std::atoll(v)) << 20;  // profiling: ncu saves
     // and restores every device buffer between replay passes

@@ -112,7 +112,14 @@ struct Ctx {
 
 }  // namespace
 
-template <int NI, bool MIX2>
+// PAGED: the variant for paged hash tables.  Paging puts a page-table read in front of every probe -- two HBM
+// round trips per nibble, one after the other (ncu, profiles/r02_m5_encode_before_prefetch_lines.txt: three
+// quarters of the history warp's time).  The encoder knows every future context, so the history warp reads
+// the two entries of the NEXT byte into registers at the start of each byte, asks L2 for the slot lines they
+// point to one nibble later, and probes through the registers when it gets there; the coder warp asks L2 for
+// the MIX2 window of the next byte a byte ahead.  The dense kernel carries none of this (its registers are
+// at the cap of 80).
+template <int NI, bool MIX2, bool PAGED = false>
 __global__ void __launch_bounds__(672, 1) k_encode_pipe3(EncodeArgs A, int blocks_per_cta) {
     extern __shared__ __align__(16) u8 smem[];
     {   // squash/stretch/next-state tables, shared by the CTA
@@ -148,6 +155,8 @@ __global__ void __launch_bounds__(672, 1) k_encode_pipe3(EncodeArgs A, int block
     int sizebits = 0;
     uint4 sl = make_uint4(0, 0, 0, 0);
     u32 pre_a = 0, pre_b = 0, sink_h = 0;
+    u32 pte_hi = 0, pte_lo = 0;    // PAGED: entries of the current byte's two slots (0: read the table)
+    u32 nxt_hi = 0, nxt_lo = 0;    // PAGED: entries of the next byte's two slots
     // C
     u16 *a16 = nullptr;
     u32 a16_mask = 0, mix_sel = 0;
@@ -244,6 +253,26 @@ __global__ void __launch_bounds__(672, 1) k_encode_pipe3(EncodeArgs A, int block
                             prefetch_l2(ht + (((k0 * 16u) & (ht_len - 16u)) & ~63u));
                             prefetch_l2(ht + (((k1 * 16u) & (ht_len - 16u)) & ~63u));
                         }
+                        if constexpr (PAGED) {
+                            // the entries read a byte ago become this byte's; read those of byte vb+1
+                            pte_hi = nxt_hi, pte_lo = nxt_lo;
+                            nxt_hi = nxt_lo = 0;
+                            if (owner && M.paged && vb + 1 < total) {
+                                const u32 *pt = reinterpret_cast<const u32 *>(ht);
+                                const u32 c1 = vbyte(vb + 1);
+                                nxt_hi = pt[(((h1 + 16u) * 16u) & (ht_len - 16u)) / kPageBytes];
+                                nxt_lo = pt[(((h1 + 16u * (16u | (c1 >> 4))) * 16u) & (ht_len - 16u)) / kPageBytes];
+                            }
+                        }
+                    } else if constexpr (PAGED) {
+                        // one nibble after they were requested: the slot lines of byte vb+1 towards L2
+                        if (owner && M.paged && vb + 1 < total) {
+                            const u32 c1 = vbyte(vb + 1);
+                            const u32 o0 = ((h1 + 16u) * 16u) & (ht_len - 16u);
+                            const u32 o1 = ((h1 + 16u * (16u | (c1 >> 4))) * 16u) & (ht_len - 16u);
+                            if (nxt_hi) prefetch_l2(M.pool + u64(nxt_hi - 1u) * kPageBytes + (o0 & (kPageBytes - 64u)));
+                            if (nxt_lo) prefetch_l2(M.pool + u64(nxt_lo - 1u) * kPageBytes + (o1 & (kPageBytes - 64u)));
+                        }
                     }
                     const u32 c8 = half ? (16u | (c >> 4)) : 1u;
                     const u32 nib = half ? (c & 15u) : (c >> 4);
@@ -257,7 +286,16 @@ __global__ void __launch_bounds__(672, 1) k_encode_pipe3(EncodeArgs A, int block
                         const u32 key = h + 16u * c8;
                         const u32 chk = (key >> sizebits) & 255u;
                         const u32 h0 = (key * 16u) & (ht_len - 16u);
-                        u8 *b0 = ht_slot(M, ht, h0);
+                        u8 *b0;
+                        if constexpr (PAGED) {
+                            // through the entry read a byte ago; a zero may be stale (the page mapped since) or
+                            // the page untouched: then the table is read, and the page mapped, as usual
+                            const u32 pte = half ? pte_lo : pte_hi;
+                            b0 = (M.paged && pte) ? M.pool + u64(pte - 1u) * kPageBytes + (h0 & (kPageBytes - 1u))
+                                                  : ht_slot(M, ht, h0);
+                        } else {
+                            b0 = ht_slot(M, ht, h0);
+                        }
                         u8 *b1 = reinterpret_cast<u8 *>(reinterpret_cast<uintptr_t>(b0) ^ 16u);
                         u8 *b2 = reinterpret_cast<u8 *>(reinterpret_cast<uintptr_t>(b0) ^ 32u);
                         sink_h += pre_a + pre_b;  // the L1 pulls of the previous step (long complete)
@@ -374,6 +412,13 @@ __global__ void __launch_bounds__(672, 1) k_encode_pipe3(EncodeArgs A, int block
                             __syncwarp();
                             for (int k = lane; k < 256; k += 32) V.a16s[k] = a16[(mix_h + u32(k)) & a16_mask];
                             __syncwarp();
+                            if constexpr (PAGED) {
+                                // the window of the NEXT byte starts at the hash of this one: ask L2 for its
+                                // nine lines a whole byte before they are staged
+                                u32 nh;
+                                const u32 hn = cx.next(cz, Z, nh);
+                                if (lane < 9) prefetch_l2(a16 + ((hn + u32(lane) * 32u) & a16_mask));
+                            }
                         }
                         // "not EOF" flag: encode(0, p=0) => low += 1 (encoder.v:108)
                         low = low + 1;
@@ -479,13 +524,18 @@ int encpipe_max_blocks_per_cta(const Model &m) {
     return g > 7 ? 7 : g;
 }
 
-template <int NI, bool MIX2>
-static bool launch_one(const EncodeArgs &A, int g, size_t smem, cudaStream_t s) {
-    auto k = k_encode_pipe3<NI, MIX2>;
+template <int NI, bool MIX2, bool PAGED>
+static bool launch_var(const EncodeArgs &A, int g, size_t smem, cudaStream_t s) {
+    auto k = k_encode_pipe3<NI, MIX2, PAGED>;
     if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)) != cudaSuccess) return false;
     const int grid = (A.n_blocks + g - 1) / g;
     k<<<grid, g * 96, smem, s>>>(A, g);
     return true;
+}
+template <int NI, bool MIX2>
+static bool launch_one(const EncodeArgs &A, int g, size_t smem, cudaStream_t s) {
+    if (A.model.paged && !(A.flags & 4)) return launch_var<NI, MIX2, true>(A, g, smem, s);
+    return launch_var<NI, MIX2, false>(A, g, smem, s);
 }
 
 bool launch_encode_pipe3(const Model &m, const EncodeArgs &A, int blocks_per_cta, cudaStream_t s) {
