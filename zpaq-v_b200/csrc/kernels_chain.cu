@@ -55,8 +55,19 @@ __device__ __forceinline__ uint4 ldg128(const u8 *p) {
 // AHEAD (serial MIX2 decoders on paged tables): what a probe will need is loaded into registers long before
 // it is needed -- page-table entries of every slot the next nibble can touch, and the sectors of the four
 // possible MIX2 weight windows of the next byte into L1 -- instead of being read when the probe is issued.
+template <bool AHEAD>
+struct AheadRegs {};
+template <>
+struct AheadRegs<true> {
+    // page-table entries of this lane's candidates for the low nibble of this byte (plo[k]: slot of
+    // c8 = 16 + 4k + pcand) and for the high nibble of the next byte (phi[k]: byte 16 hi + 4k + pcand), k = the
+    // two bits that are decoded before the probe is issued; L1 pulls in flight
+    u32 plo0, plo1, plo2, plo3, phi0, phi1, phi2, phi3;
+    u32 pull_a, pull_b, pull_sink;
+};
+
 template <int NI, bool MIX2, bool AHEAD = false>
-struct ProbeBase {
+struct ProbeBase : AheadRegs<AHEAD> {
     // shared-memory views
     const int16_t *stretch;  // padded: entry 0 holds entry 1
     const u16 *squash;       // padded: indexed by p + 2048
@@ -86,19 +97,17 @@ struct ProbeBase {
     u8 *qb0;
     u32 q_key, cur_vline;    // cur_vline: 64-byte line (virtual offset >> 6) of the current slot
     bool q_ok, spec;
-    // AHEAD: page-table entries of this lane's candidates for the low nibble of this byte (plo[k]: slot of
-    // c8 = 16 + 4k + pcand) and for the high nibble of the next byte (phi[k]: byte 16 hi + 4k + pcand), k = the
-    // two bits that are decoded before the probe is issued; L1 pulls in flight
-    u32 plo[4], phi[4];
-    u32 pull_a, pull_b, pull_sink;
 
     __device__ void base_setup(const ModelDev &M, u8 *ws, const int16_t *st, const u16 *sq, const u8 *nx) {
         lane = threadIdx.x & 31;
         pc = lane & 7, pcand = u32(lane) >> 3;
         powner = pc <= NI;
         spec = true, q_ok = false, qb0 = nullptr, q_key = 0, cur_vline = ~0u;
-        for (int k = 0; k < 4; ++k) plo[k] = phi[k] = 0;
-        pull_a = pull_b = pull_sink = 0;
+        if constexpr (AHEAD) {
+            this->plo0 = this->plo1 = this->plo2 = this->plo3 = 0;
+            this->phi0 = this->phi1 = this->phi2 = this->phi3 = 0;
+            this->pull_a = this->pull_b = this->pull_sink = 0;
+        }
         q0 = q1 = q2 = make_uint4(0, 0, 0, 0);
         stretch = st, squash = sq, nex16 = reinterpret_cast<const u16 *>(nx);
         ctx_mode = M.ctx_mode, n_hash = M.n_hash, n_comp = M.n;
@@ -192,8 +201,10 @@ struct ProbeBase {
             const u32 *pt = reinterpret_cast<const u32 *>(ht);
             const u32 np = max(ht_len / kPageBytes, 1u);
             const u32 first = (((h + 256u) * 16u) & (ht_len - 16u)) / kPageBytes;
-#pragma unroll
-            for (u32 k = 0; k < 4; ++k) plo[k] = pt[(first + 4u * k + pcand) & (np - 1u)];
+            this->plo0 = pt[(first + pcand) & (np - 1u)];
+            this->plo1 = pt[(first + 4u + pcand) & (np - 1u)];
+            this->plo2 = pt[(first + 8u + pcand) & (np - 1u)];
+            this->plo3 = pt[(first + 12u + pcand) & (np - 1u)];
         }
     }
 
@@ -202,12 +213,12 @@ struct ProbeBase {
     __device__ __forceinline__ void load_phi(u32 hi) {
         if (md->paged && powner && spec) {
             const u32 *pt = reinterpret_cast<const u32 *>(ht);
-#pragma unroll
-            for (u32 k = 0; k < 4; ++k) {
+            auto entry = [&](u32 k) {
                 u32 nh, mixv;
                 const u32 key = ctx_next(hi * 16u + k * 4u + pcand, pc, nh, mixv) + 16u;
-                phi[k] = pt[((key * 16u) & (ht_len - 16u)) / kPageBytes];
-            }
+                return pt[((key * 16u) & (ht_len - 16u)) / kPageBytes];
+            };
+            this->phi0 = entry(0), this->phi1 = entry(1), this->phi2 = entry(2), this->phi3 = entry(3);
         }
     }
 
@@ -231,13 +242,13 @@ struct ProbeBase {
                 // the MIX2 weights of the next byte are a 512-byte window starting at its context hash: the
                 // eight lanes of a candidate pull its sixteen 32-byte sectors into L1 (two 4-byte loads each,
                 // nobody waits for them), so stage_mix at the byte boundary finds them there
-                pull_sink += pull_a + pull_b;  // those of the previous byte, long complete
+                this->pull_sink += this->pull_a + this->pull_b;  // those of the previous byte, long complete
                 u32 nh, mixv;
                 ctx_next(((c8part << 2) | pcand) & 255u, pc, nh, mixv);
                 const u16 *w0 = a16 + (((mixv & ~1u) + u32(pc) * 32u) & a16_mask);
                 const u16 *w1 = a16 + (((mixv & ~1u) + u32(pc) * 32u + 16u) & a16_mask);
-                asm volatile("ld.global.ca.u32 %0, [%1];" : "=r"(pull_a) : "l"(w0));
-                asm volatile("ld.global.ca.u32 %0, [%1];" : "=r"(pull_b) : "l"(w1));
+                asm volatile("ld.global.ca.u32 %0, [%1];" : "=r"(this->pull_a) : "l"(w0));
+                asm volatile("ld.global.ca.u32 %0, [%1];" : "=r"(this->pull_b) : "l"(w1));
             }
         }
         if (powner && spec) {
@@ -255,8 +266,8 @@ struct ProbeBase {
                 // then nothing is requested early and choose() reads the table itself.
                 if (md->paged) {
                     const u32 k = c8part & 3u;
-                    const u32 sel_lo = k == 0 ? plo[0] : k == 1 ? plo[1] : k == 2 ? plo[2] : plo[3];
-                    const u32 sel_hi = k == 0 ? phi[0] : k == 1 ? phi[1] : k == 2 ? phi[2] : phi[3];
+                    const u32 sel_lo = k == 0 ? this->plo0 : k == 1 ? this->plo1 : k == 2 ? this->plo2 : this->plo3;
+                    const u32 sel_hi = k == 0 ? this->phi0 : k == 1 ? this->phi1 : k == 2 ? this->phi2 : this->phi3;
                     const u32 pte = c8new < 256u ? sel_lo : sel_hi;
                     b0 = pte ? md->pool + u64(pte - 1u) * kPageBytes + (h0 & (kPageBytes - 1u)) : nullptr;
                 } else {
