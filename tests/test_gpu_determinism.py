@@ -31,11 +31,13 @@ def _blocks(n):
 
 @pytest.mark.parametrize("level", [1, 2, 4])
 def test_same_bytes_under_every_packing(gpu_ctx, level):
-    blocks = _blocks(1040)
+    # (the oracle sets up 385 MiB of tables per block at -m4: fewer blocks there)
+    top = 1040 if level < 4 else 300
+    blocks = _blocks(top)
     want = None
-    packings = [(37, 0, 0), (600, 0, 0), (1040, 0, 0), (1040, 2, 0)]
+    packings = [(37, 0, 0), (top, 0, 0), (top, 2, 0)]
     if level < 4:
-        packings += [(1040, 1, 2), (600, 2, 1)]   # dense in waves of what 2 GiB hold; paged with a 1 GiB budget
+        packings += [(600, 0, 0), (1040, 1, 2), (600, 2, 1)]   # dense in waves of what 2 GiB hold; paged with a 1 GiB budget
     for n, mode, limit_gib in packings:
         gpu_ctx.set_table_mode(mode)
         gpu_ctx.set_workspace_limit(limit_gib << 30)

@@ -644,7 +644,7 @@ int run_decompress(zpaqgpu_ctx *ctx, DecompressJob &job, bool caller_owns_plain)
                             da.seg_count = static_cast<u32 *>(ctx->misc.p);
                             da.seg_cap = seg_cap, da.first_block = first, da.n_blocks = cnt;
                             da.order = reinterpret_cast<const u32 *>(static_cast<const u8 *>(ctx->desc.p) + o_dorder);
-                            da.flags = (ctx->spec_probe ? 1 : 0) | (ctx->ahead ? 0 : 2) | (ctx->guess << 8) | (ctx->pull_how << 12);
+                            da.flags = (ctx->spec_probe ? 1 : 0) | (ctx->guess << 8) | (ctx->pull_how << 12);
                             CK(cudaEventRecord(ctx->ev[0], st));
                             if (store) {
                                 da.model = mod.dense;

@@ -52,7 +52,7 @@ struct zpaqgpu_ctx {
     int pull_how = 0;          // ZPAQGPU_PULL: how (experiments)
     int guess = 1;             // ZPAQGPU_GUESS=n: the two-warp decoder pulls the n (0, 1, 2, 4) likeliest next slot lines a nibble early
     bool generic_warp = true;  // ZPAQGPU_GENERIC=lane0: the one-lane generic kernels also for headers the warp kernel takes (A/B)
-    bool ahead = true;         // ZPAQGPU_AHEAD=0: paged -m4/-m5 decoders and encoders read page-table entries when they probe (A/B)
+    bool ahead = true;         // ZPAQGPU_AHEAD=0: the encoder on paged tables reads page-table entries when it probes (A/B against the PAGED variant)
     bool spec_probe = true;    // ZPAQGPU_SPEC_PROBE=0: the chain decoders probe only once a nibble is complete
     int decoder = 1;           // ZPAQGPU_DECODER in the environment: serial (0, one bit at a time), tree (1, one warp per
                                // block), tree2 (2, two warps per block; the default where the model allows it)

@@ -52,22 +52,8 @@ __device__ __forceinline__ uint4 ldg128(const u8 *p) {
 // pcand = lane >> 3): the four lanes of a component hold its table geometry and context hash, request
 // the four possible slot lines of the next nibble two bits early (probe_issue) and make the find_ht
 // choice (choose) from registers when their guess was right.
-// AHEAD (serial MIX2 decoders on paged tables): what a probe will need is loaded into registers long before
-// it is needed -- page-table entries of every slot the next nibble can touch, and the sectors of the four
-// possible MIX2 weight windows of the next byte into L1 -- instead of being read when the probe is issued.
-template <bool AHEAD>
-struct AheadRegs {};
-template <>
-struct AheadRegs<true> {
-    // page-table entries of this lane's candidates for the low nibble of this byte (plo[k]: slot of
-    // c8 = 16 + 4k + pcand) and for the high nibble of the next byte (phi[k]: byte 16 hi + 4k + pcand), k = the
-    // two bits that are decoded before the probe is issued; L1 pulls in flight
-    u32 plo0, plo1, plo2, plo3, phi0, phi1, phi2, phi3;
-    u32 pull_a, pull_b, pull_sink;
-};
-
-template <int NI, bool MIX2, bool AHEAD = false>
-struct ProbeBase : AheadRegs<AHEAD> {
+template <int NI, bool MIX2>
+struct ProbeBase {
     // shared-memory views
     const int16_t *stretch;  // padded: entry 0 holds entry 1
     const u16 *squash;       // padded: indexed by p + 2048
@@ -103,11 +89,6 @@ struct ProbeBase : AheadRegs<AHEAD> {
         pc = lane & 7, pcand = u32(lane) >> 3;
         powner = pc <= NI;
         spec = true, q_ok = false, qb0 = nullptr, q_key = 0, cur_vline = ~0u;
-        if constexpr (AHEAD) {
-            this->plo0 = this->plo1 = this->plo2 = this->plo3 = 0;
-            this->phi0 = this->phi1 = this->phi2 = this->phi3 = 0;
-            this->pull_a = this->pull_b = this->pull_sink = 0;
-        }
         q0 = q1 = q2 = make_uint4(0, 0, 0, 0);
         stretch = st, squash = sq, nex16 = reinterpret_cast<const u16 *>(nx);
         ctx_mode = M.ctx_mode, n_hash = M.n_hash, n_comp = M.n;
@@ -145,7 +126,6 @@ struct ProbeBase : AheadRegs<AHEAD> {
         h = 0, mix_h = 0;
         q_ok = false;  // requested with the old contexts
         stage_mix();
-        if constexpr (AHEAD) load_plo();
     }
 
     __device__ void stage_mix() {
@@ -190,36 +170,6 @@ struct ProbeBase : AheadRegs<AHEAD> {
             mix_h = mixv;
             stage_mix();
         }
-        if constexpr (AHEAD) load_plo();
-    }
-
-    // AHEAD, byte boundary: the 16 possible slots of this byte's LOW nibble (keys h + 16 * (16..31)) are 256
-    // bytes apart, one page each, so their page-table entries are 16 consecutive words; this lane will probe
-    // c8 = 16 + 4k + pcand once the two bits k are decoded.
-    __device__ __forceinline__ void load_plo() {
-        if (md->paged && powner && spec) {
-            const u32 *pt = reinterpret_cast<const u32 *>(ht);
-            const u32 np = max(ht_len / kPageBytes, 1u);
-            const u32 first = (((h + 256u) * 16u) & (ht_len - 16u)) / kPageBytes;
-            this->plo0 = pt[(first + pcand) & (np - 1u)];
-            this->plo1 = pt[(first + 4u + pcand) & (np - 1u)];
-            this->plo2 = pt[(first + 8u + pcand) & (np - 1u)];
-            this->plo3 = pt[(first + 12u + pcand) & (np - 1u)];
-        }
-    }
-
-    // AHEAD, start of the low nibble (high nibble `hi` decoded): the next byte is one of 16; this lane will
-    // probe the high-nibble slot of byte 16 hi + 4k + pcand once the two bits k are decoded.
-    __device__ __forceinline__ void load_phi(u32 hi) {
-        if (md->paged && powner && spec) {
-            const u32 *pt = reinterpret_cast<const u32 *>(ht);
-            auto entry = [&](u32 k) {
-                u32 nh, mixv;
-                const u32 key = ctx_next(hi * 16u + k * 4u + pcand, pc, nh, mixv) + 16u;
-                return pt[((key * 16u) & (ht_len - 16u)) / kPageBytes];
-            };
-            this->phi0 = entry(0), this->phi1 = entry(1), this->phi2 = entry(2), this->phi3 = entry(3);
-        }
     }
 
     // Address of a slot without side effects: nullptr when a paged table has no page there yet.
@@ -237,20 +187,6 @@ struct ProbeBase : AheadRegs<AHEAD> {
     // not requested (it changes at the write-back), nor an unmapped page.
     __device__ __forceinline__ void probe_issue(u32 c8part) {
         q_ok = false;
-        if constexpr (AHEAD && MIX2) {
-            if (spec && (c8part << 2) >= 256u) {
-                // the MIX2 weights of the next byte are a 512-byte window starting at its context hash: the
-                // eight lanes of a candidate pull its sixteen 32-byte sectors into L1 (two 4-byte loads each,
-                // nobody waits for them), so stage_mix at the byte boundary finds them there
-                this->pull_sink += this->pull_a + this->pull_b;  // those of the previous byte, long complete
-                u32 nh, mixv;
-                ctx_next(((c8part << 2) | pcand) & 255u, pc, nh, mixv);
-                const u16 *w0 = a16 + (((mixv & ~1u) + u32(pc) * 32u) & a16_mask);
-                const u16 *w1 = a16 + (((mixv & ~1u) + u32(pc) * 32u + 16u) & a16_mask);
-                asm volatile("ld.global.ca.u32 %0, [%1];" : "=r"(this->pull_a) : "l"(w0));
-                asm volatile("ld.global.ca.u32 %0, [%1];" : "=r"(this->pull_b) : "l"(w1));
-            }
-        }
         if (powner && spec) {
             const u32 c8new = (c8part << 2) | pcand;
             if (c8new < 256u) {
@@ -260,22 +196,7 @@ struct ProbeBase : AheadRegs<AHEAD> {
                 q_key = ctx_next(c8new & 255u, pc, nh, mixv) + 16u;
             }
             const u32 h0 = (q_key * 16u) & (ht_len - 16u);
-            u8 *b0;
-            if constexpr (AHEAD) {
-                // the entry was read into a register a nibble ago.  A zero may be stale (the page mapped since):
-                // then nothing is requested early and choose() reads the table itself.
-                if (md->paged) {
-                    const u32 k = c8part & 3u;
-                    const u32 sel_lo = k == 0 ? this->plo0 : k == 1 ? this->plo1 : k == 2 ? this->plo2 : this->plo3;
-                    const u32 sel_hi = k == 0 ? this->phi0 : k == 1 ? this->phi1 : k == 2 ? this->phi2 : this->phi3;
-                    const u32 pte = c8new < 256u ? sel_lo : sel_hi;
-                    b0 = pte ? md->pool + u64(pte - 1u) * kPageBytes + (h0 & (kPageBytes - 1u)) : nullptr;
-                } else {
-                    b0 = ht + h0;
-                }
-            } else {
-                b0 = slot_peek(h0);
-            }
+            u8 *b0 = slot_peek(h0);
             if (b0 && (h0 >> 6) != cur_vline) {
                 qb0 = b0;
                 q0 = ldg128(b0);
@@ -330,9 +251,9 @@ struct ProbeBase : AheadRegs<AHEAD> {
 };
 
 // Serial decoder state: one model component per lane (lane i = component i, i <= NI).
-template <int NI, bool MIX2, bool AHEAD = false>
-struct Chain : ProbeBase<NI, MIX2, AHEAD> {
-    using B = ProbeBase<NI, MIX2, AHEAD>;
+template <int NI, bool MIX2>
+struct Chain : ProbeBase<NI, MIX2> {
+    using B = ProbeBase<NI, MIX2>;
     int2 *tab;         // this lane's table: ICM {cm[s], stretch(cm[s]>>8)} or ISSE {wt0, wt1}
     int2 *dump;        // 32 entries nobody reads
     u8 *slot_at;       // where the parked slot lives in HBM (nullptr: none yet)
@@ -378,8 +299,8 @@ struct Chain : ProbeBase<NI, MIX2, AHEAD> {
 // Four coded bits of one nibble, whole warp converged (predictor.v:536-824 for the ICM/ISSE/MIX2
 // chain, encoder.v:48-89 / decoder.v:73-118).  ENC: `nib` holds the 4 bits, MSB first; DEC: returns
 // them.  c8 enters as 1 (high nibble) or 16..31 (low nibble).
-template <int NI, bool MIX2, bool DEC, class CH, class IO>
-__device__ __forceinline__ u32 code_nibble(CH &C, u32 nib, u32 &c8, u32 &low, u32 &high,
+template <int NI, bool MIX2, bool DEC, class IO>
+__device__ __forceinline__ u32 code_nibble(Chain<NI, MIX2> &C, u32 nib, u32 &c8, u32 &low, u32 &high,
                                            u32 &code, IO &io) {
     const int lane = C.lane;
     u32 idx = 1;
@@ -703,7 +624,7 @@ __device__ __forceinline__ void load_shared_tables(u8 *smem, const DevTables &T)
 // ------------------------------------------------------------------------------------------
 // k_decode_chain
 // ------------------------------------------------------------------------------------------
-template <int NI, bool MIX2, bool TREE, bool AHEAD = false>
+template <int NI, bool MIX2, bool TREE>
 __global__ void __launch_bounds__(256, 1) k_decode_chain(DecodeArgs A) {
     extern __shared__ __align__(16) u8 smem[];
     load_shared_tables(smem, A.tables);
@@ -711,7 +632,7 @@ __global__ void __launch_bounds__(256, 1) k_decode_chain(DecodeArgs A) {
     const int slot = blockIdx.x * (blockDim.x >> 5) + wic;
     if (slot >= A.n_blocks) return;
     const int bi = int(A.order[A.first_block + slot]);
-    typename std::conditional<TREE, Tree<NI, MIX2>, Chain<NI, MIX2, AHEAD>>::type C;
+    typename std::conditional<TREE, Tree<NI, MIX2>, Chain<NI, MIX2>>::type C;
     u8 *ws = A.workspace + u64(slot) * A.model.ws_bytes;
     C.setup(smem + kSharedTables + size_t(wic) * warp_smem_bytes(NI, MIX2), A.model, ws,
             reinterpret_cast<const int16_t *>(smem), reinterpret_cast<const u16 *>(smem + 65536),
@@ -770,9 +691,6 @@ __global__ void __launch_bounds__(256, 1) k_decode_chain(DecodeArgs A) {
 #pragma unroll 1
             for (int half = 0; half < 2; ++half) {
                 C.probe(c8);
-                if constexpr (AHEAD) {
-                    if (half == 1) C.load_phi(c8 & 15u);
-                }
                 if constexpr (TREE) decode_nibble_tree<NI, MIX2>(C, c8, low, high, code, io);
                 else code_nibble<NI, MIX2, true>(C, 0, c8, low, high, code, io);
             }
@@ -836,9 +754,6 @@ __global__ void __launch_bounds__(256, 1) k_decode_chain(DecodeArgs A) {
     if (pos > A.arc_len) pos = A.arc_len;
     res.end_pos = pos;
     if (lane == 0) A.results[bi] = res;
-    if constexpr (AHEAD) {
-        if (C.pull_sink + C.pull_a + C.pull_b == 0x9E3779B9u && A.n_blocks < 0) A.results[0].status = 1;  // keeps the pulls
-    }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -854,10 +769,10 @@ int chain_max_warps_per_cta(const Model &m) {
     return w > 8 ? 8 : w;
 }
 
-template <int NI, bool MIX2, bool TREE, bool AHEAD = false>
+template <int NI, bool MIX2, bool TREE>
 static bool launch_dec(const DecodeArgs &D, int wpc, size_t smem, cudaStream_t s) {
     const int grid = (D.n_blocks + wpc - 1) / wpc;
-    auto k = k_decode_chain<NI, MIX2, TREE, AHEAD>;
+    auto k = k_decode_chain<NI, MIX2, TREE>;
     if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)) != cudaSuccess) return false;
     k<<<grid, wpc * 32, smem, s>>>(D);
     return true;
@@ -871,12 +786,6 @@ bool launch_decode_chain(const Model &m, const DecodeArgs &A, int wpc, bool tree
     // (-16/-15/-11 % kernel time) and loses at -m4/-m5 (six and eight components plus MIX2, +33/+30 %).
     // It also takes MIX2 weights per node from the staged copy, which needs mask 255.
     if (m.has_mix2 || m.n_isse > 4) tree = false;
-    // serial MIX2 decoders on paged tables (-m4/-m5 when the dense tables do not fit): the AHEAD variant
-    const bool ahead = !tree && m.has_mix2 && A.model.paged && !(A.flags & 2);
-#define ZG_AHEAD(NI)                                                           \
-    if (ahead && m.n_isse == NI) return launch_dec<NI, true, false, true>(A, wpc, smem, s);
-    ZG_AHEAD(2) ZG_AHEAD(3) ZG_AHEAD(4) ZG_AHEAD(5) ZG_AHEAD(6) ZG_AHEAD(7)
-#undef ZG_AHEAD
 #define ZG_CASE(NI, MX)                                                        \
     if (m.n_isse == NI && m.has_mix2 == MX)                                    \
         return tree ? launch_dec<NI, MX, true>(A, wpc, smem, s) : launch_dec<NI, MX, false>(A, wpc, smem, s);
