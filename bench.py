@@ -546,23 +546,50 @@ def run_per_level(args, E):
     out = {}
 
     def one(key, level, data_np, nb, bb, scaling, what, warm_blocks=148):
-        """data_np: this rank's input (nb * bb bytes, host)."""
-        codec = DeviceCodec(E["z"], E["zb"], torch, dev, torch.cuda.current_stream().cuda_stream)
-        try:
-            total = nb * bb
-            if not data_np.flags.writeable:
-                data_np = data_np.copy()
-            d_in = torch.from_numpy(data_np).to(dev)
+        """data_np: this rank's input (nb * bb bytes, host).  Every rank reaches every collective: a failure on
+        one rank (say, out of memory) is agreed on through the max-reduction instead of leaving the others at a
+        barrier."""
+        codec = None
+        state = {}
+
+        def attempt(fn):
+            err = None
+            try:
+                fn()
+            except SystemExit:
+                raise
+            except Exception as ex:
+                err = "%s: %s" % (type(ex).__name__, ex)
+            bad = E["allmax"]([1.0 if err else 0.0])[0] > 0
+            return err if err else ("another rank failed" if bad else None)
+
+        def setup():
+            nonlocal codec
+            codec = DeviceCodec(E["z"], E["zb"], torch, dev, torch.cuda.current_stream().cuda_stream)
+            data = data_np if data_np.flags.writeable else data_np.copy()
+            state["d_in"] = torch.from_numpy(data).to(dev)
             # a small pass first: module load, first-touch of the constant tables, buffer growth
             wb = min(nb, warm_blocks)
+            state["wb"] = wb
             codec.alloc(wb, bb, slack=2)
-            codec.step(level, d_in[:wb * bb])
+            codec.step(level, state["d_in"][:wb * bb])
             codec.alloc(nb, bb, slack=2 if level == 3 else 4)
-            E["barrier"]()
-            t_c, t_d, arc, st_c, st_d = codec.step(level, d_in)
-            E["barrier"]()
-            if not torch.equal(codec.d_plain, d_in):
-                raise SystemExit("per-level %s: round trip mismatch" % key)
+
+        def timed():
+            state["res"] = codec.step(level, state["d_in"])
+            if not torch.equal(codec.d_plain, state["d_in"]):
+                raise RuntimeError("round trip mismatch")
+
+        try:
+            total = nb * bb
+            err = attempt(setup)
+            if not err:
+                E["barrier"]()
+                err = attempt(timed)
+            if err:
+                return {"what": what, "level": level, "error": err}
+            t_c, t_d, arc, st_c, st_d = state["res"]
+            wb = state["wb"]
             idx = sorted(set(int(x) for x in np.linspace(0, nb - 1, 8)))
             ok = bool(parity_blocks(codec, level, data_np, idx, E["cores"])) if rank == 0 else None
             m_c, m_d, k_c, k_d = E["allmax"]([t_c, t_d, st_c["codec_ms"] / 1e3, st_d["codec_ms"] / 1e3])
@@ -586,11 +613,14 @@ def run_per_level(args, E):
                 "pool_mb_used": [round(st_c["pool_bytes_used"] / 1e6, 1), round(st_d["pool_bytes_used"] / 1e6, 1)],
                 "warps_per_cta": [st_c["warps_per_cta"], st_d["warps_per_cta"]],
                 "byte_identical_to_oracle": ok, "parity_blocks": idx, "round_trip_exact": True,
-                "timing": "one pass after a %d-block warm-up pass; CUDA events" % wb,
+                "timing": "one pass after a %d-block warm-up pass; CUDA events; kernel figures = the codec kernel alone, "
+                          "the others the whole device-pointer call (table clearing, SHA-1, assembly included)" % wb,
             }
         finally:
-            codec.close()
-            del codec
+            if codec is not None:
+                codec.close()
+            codec = None
+            state.clear()
             torch.cuda.empty_cache()
 
     text = E["text"]  # this rank's 1 GiB (or --blocks x --block-kib) of the text stream
@@ -632,9 +662,10 @@ def run_per_level(args, E):
                 out["generic"] = run_generic(args, E)
         except SystemExit:
             raise
-        except Exception as ex:  # a configuration that cannot run is reported, never silently dropped
-            name = {"jidac": "jidac_add", "generic": "generic"}.get(key, "m" + key)
-            out[name] = {"error": "%s: %s" % (type(ex).__name__, ex)}
+        except Exception as ex:  # rank-0-only sections (jidac, generic): reported, never silently dropped
+            if key not in ("jidac", "generic"):
+                raise
+            out[{"jidac": "jidac_add", "generic": "generic"}[key]] = {"error": "%s: %s" % (type(ex).__name__, ex)}
             torch.cuda.empty_cache()
     E["barrier"]()
     return out
