@@ -132,8 +132,12 @@ struct TablePlan {
     u64 pool_bytes = 0;
 };
 
+// round_cap: how many blocks the codec kernel holds at once (SMs x blocks per CTA; 0 = do not care).  A dense
+// wave larger than that runs its CTAs in two rounds, the second nearly empty: a batch of several waves is
+// therefore cut into as few rounds as its size needs, all of the same size (8 192 blocks at -m3: memory
+// would take 1 127 per wave = 161 encoder CTAs on 148 SMs; 8 waves of 1 024 = 147 CTAs each instead).
 int plan_tables(zpaqgpu_ctx *ctx, const Model &m, int n_blocks, size_t other_bytes, bool chain, bool force_dense,
-                TablePlan &tp) {
+                int round_cap, TablePlan &tp) {
     size_t free_b = 0, total_b = 0;
     CK(cudaMemGetInfo(&free_b, &total_b));
     free_b += ctx->workspace.cap + ctx->pool.cap;  // our own cached buffers can be reused
@@ -166,7 +170,13 @@ int plan_tables(zpaqgpu_ctx *ctx, const Model &m, int n_blocks, size_t other_byt
         ctx->err = "model tables (" + std::to_string(m.ws_bytes) + " bytes per block) exceed the workspace budget";
         return ZPAQGPU_E_NOMEM;
     }
-    tp.paged = false, tp.slots = int(std::min<u64>(dense_slots, u64(n_blocks))), tp.stride = m.ws_bytes, tp.pool_bytes = 0;
+    u64 slots = std::min<u64>(dense_slots, u64(n_blocks));
+    if (round_cap > 0 && u64(n_blocks) > slots) {
+        const u64 per_round = std::min<u64>(slots, u64(round_cap));
+        const u64 rounds = (u64(n_blocks) + per_round - 1) / per_round;
+        slots = (u64(n_blocks) + rounds - 1) / rounds;
+    }
+    tp.paged = false, tp.slots = int(slots), tp.stride = m.ws_bytes, tp.pool_bytes = 0;
     return ZPAQGPU_OK;
 }
 
@@ -332,7 +342,8 @@ int run_compress(zpaqgpu_ctx *ctx, CompressJob &job) {
             bool force_dense = false;
             for (int table_try = 0; table_try < 2; ++table_try) {
                 TablePlan tp;
-                if ((rc = plan_tables(ctx, m, n_blocks, arena_bytes, chain, force_dense, tp))) return rc;
+                const int round_cap = chain ? ctx->sm_count * encpipe_max_blocks_per_cta(m) : 0;
+                if ((rc = plan_tables(ctx, m, n_blocks, arena_bytes, chain, force_dense, round_cap, tp))) return rc;
                 if ((rc = ensure_tables(ctx, u64(tp.slots) * tp.stride, tp.paged ? tp.pool_bytes : 0))) return rc;
                 // encoder: three warps per block, as many blocks per CTA as spreads the wave over all SMs
                 int wpc = 4;
@@ -617,7 +628,11 @@ int run_decompress(zpaqgpu_ctx *ctx, DecompressJob &job, bool caller_owns_plain)
                         TablePlan tp;
                         tp.slots = run;
                         if (!store) {
-                            if ((rc = plan_tables(ctx, m, run, plain_bytes, chain, dense_only, tp))) return rc;
+                            const int round_cap =
+                                !chain ? 0
+                                       : ctx->sm_count * ((ctx->decoder == 2 && tree2_supports(m)) ? tree2_max_pairs_per_cta(m)
+                                                                                                    : chain_max_warps_per_cta(m));
+                            if ((rc = plan_tables(ctx, m, run, plain_bytes, chain, dense_only, round_cap, tp))) return rc;
                             if ((rc = ensure_tables(ctx, u64(tp.slots) * tp.stride, tp.paged ? tp.pool_bytes : 0)))
                                 return rc;
                             ctx->stats.paged = tp.paged ? 1 : 0;
