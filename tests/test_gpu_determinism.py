@@ -35,13 +35,13 @@ def test_same_bytes_under_every_packing(gpu_ctx, level):
     top = 1040 if level < 4 else 300
     blocks = _blocks(top)
     want = None
-    packings = [(37, 0, 0), (top, 0, 0), (top, 2, 0)]
+    packings = [(37, 0, 0, 1), (top, 0, 0, 2), (top, 2, 0, 1)]
     if level < 4:
-        packings += [(600, 0, 0), (1040, 1, 2), (600, 2, 1)]   # dense in waves of what 2 GiB hold; paged with a 1 GiB budget
-    for n, mode, limit_gib in packings:
+        packings += [(600, 0, 0, 1), (1040, 1, 2, 1)]   # five blocks per CTA; dense in waves of what 2 GiB hold
+    for n, mode, limit_gib, reps in packings:
         gpu_ctx.set_table_mode(mode)
         gpu_ctx.set_workspace_limit(limit_gib << 30)
-        for rep in range(2):
+        for rep in range(reps):
             got = gpu_ctx.compress_blocks(level, blocks[:n])
             if want is None:
                 want = [ob.compress_block(level, b, "", "") for b in blocks]
