@@ -35,9 +35,10 @@ def test_same_bytes_under_every_packing(gpu_ctx, level):
     top = 1040 if level < 4 else 300
     blocks = _blocks(top)
     want = None
-    packings = [(37, 0, 0, 1), (top, 0, 0, 2), (top, 2, 0, 1)]
+    # 1 block per CTA; 3 per CTA twice; paged; and, where the tables allow, 7 per CTA and dense waves of what 2 GiB hold
+    packings = [(37, 0, 0, 1), (300, 0, 0, 2), (300, 2, 0, 1)]
     if level < 4:
-        packings += [(600, 0, 0, 1), (1040, 1, 2, 1)]   # five blocks per CTA; dense in waves of what 2 GiB hold
+        packings += [(1040, 0, 0, 1), (300, 1, 2, 1)]
     for n, mode, limit_gib, reps in packings:
         gpu_ctx.set_table_mode(mode)
         gpu_ctx.set_workspace_limit(limit_gib << 30)
