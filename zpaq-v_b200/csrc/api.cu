@@ -214,10 +214,20 @@ bool use_chain(const zpaqgpu_ctx *ctx, const Model &m) {
     return m.is_chain;
 }
 
+// Blocks per CTA of a launch of n blocks when a CTA can hold at most `most` (one CTA per SM: shared memory):
+// as many as spread the launch over all SMs; when that is more than a CTA holds, the CTAs run in rounds, and
+// the rounds are made equal instead of a full one followed by a nearly empty one (-m5 encoder: 1 024 blocks,
+// 6 per CTA at most = 171 CTAs on 148 SMs; 4 per CTA = two rounds of 128).
+int per_cta(const zpaqgpu_ctx *ctx, int n, int most) {
+    const int sms = std::max(1, ctx->sm_count);
+    const int per_sm = (n + sms - 1) / sms;
+    if (per_sm <= most) return std::max(1, per_sm);
+    const int rounds = (n + sms * most - 1) / (sms * most);
+    return std::max(1, std::min(most, (n + rounds * sms - 1) / (rounds * sms)));
+}
+
 int pick_warps_per_cta(const zpaqgpu_ctx *ctx, const Model &m, int n_resident) {
-    const int wmax = chain_max_warps_per_cta(m);
-    int w = (n_resident + ctx->sm_count - 1) / ctx->sm_count;
-    return std::max(1, std::min(wmax, w));
+    return per_cta(ctx, n_resident, chain_max_warps_per_cta(m));
 }
 
 float elapsed(cudaEvent_t a, cudaEvent_t b) {
@@ -347,10 +357,7 @@ int run_compress(zpaqgpu_ctx *ctx, CompressJob &job) {
                 if ((rc = ensure_tables(ctx, u64(tp.slots) * tp.stride, tp.paged ? tp.pool_bytes : 0))) return rc;
                 // encoder: three warps per block, as many blocks per CTA as spreads the wave over all SMs
                 int wpc = 4;
-                if (chain) {
-                    const int per_sm = (tp.slots + ctx->sm_count - 1) / ctx->sm_count;
-                    wpc = std::max(1, std::min(encpipe_max_blocks_per_cta(m), per_sm));
-                }
+                if (chain) wpc = per_cta(ctx, tp.slots, encpipe_max_blocks_per_cta(m));
                 ctx->stats.warps_per_cta = chain ? wpc * 3 : wpc;
                 ctx->stats.paged = tp.paged ? 1 : 0;
                 ctx->stats.workspace_bytes_per_block = tp.stride;
@@ -640,10 +647,7 @@ int run_decompress(zpaqgpu_ctx *ctx, DecompressJob &job, bool caller_owns_plain)
                         }
                         const bool tree2 = chain && ctx->decoder == 2 && tree2_supports(m);
                         int wpc = chain ? pick_warps_per_cta(ctx, m, tp.slots) : 4;
-                        if (tree2) {
-                            const int per_sm = (tp.slots + ctx->sm_count - 1) / ctx->sm_count;
-                            wpc = std::max(1, std::min(tree2_max_pairs_per_cta(m), per_sm));
-                        }
+                        if (tree2) wpc = per_cta(ctx, tp.slots, tree2_max_pairs_per_cta(m));
                         ctx->stats.warps_per_cta = tree2 ? 2 * wpc : wpc;
                         bool overflow = false;
                         for (int first = i; first < j && !overflow; first += tp.slots) {
