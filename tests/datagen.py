@@ -93,11 +93,15 @@ def text_range(first, n, seed=SEED0, threads=None):
     _vocab_arrays()
     ids = list(range(c0, c1 + 1))
     workers = threads or min(len(ids), os.cpu_count() or 1)
+    # a chunk's bytes do not depend on how many of them are generated (the random stream and the word layout
+    # are prefix-stable), so the last chunk is only made as long as the range needs
+    need = {k: CHUNK for k in ids}
+    need[c1] = first + n - c1 * CHUNK
     if workers > 1:
         with ThreadPoolExecutor(workers) as ex:
-            parts = list(ex.map(lambda k: _text_chunk(CHUNK, seed + 0x9E37 * k), ids))
+            parts = list(ex.map(lambda k: _text_chunk(need[k], seed + 0x9E37 * k), ids))
     else:
-        parts = [_text_chunk(CHUNK, seed + 0x9E37 * k) for k in ids]
+        parts = [_text_chunk(need[k], seed + 0x9E37 * k) for k in ids]
     whole = np.concatenate(parts) if len(parts) > 1 else parts[0]
     lo = first - c0 * CHUNK
     return whole[lo:lo + n].tobytes()

@@ -9,7 +9,7 @@ equal the CPU oracle's bytes.  (-m4 runs paged: its dense tables are 385 MiB per
 import pytest
 
 import datagen
-import oracle_binding as ob
+from test_gpu_fullsize import oracle_blocks_mt
 
 pytestmark = pytest.mark.gpu
 
@@ -22,10 +22,16 @@ def _reset(gpu_ctx):
 
 
 def _blocks(n):
-    out = []
-    for k in range(n):
-        size = 1500 + (k * 397) % 2600
-        out.append(datagen.mixed_block(k, size, datagen.SEED0 + 500))
+    """n blocks of 1.5-4 KB: text, text, random, structured, ... cut from three buffers made once (a
+    datagen call builds an 8 MiB chunk, so one call per block would cost minutes)."""
+    sizes = [1500 + (k * 397) % 2600 for k in range(n)]
+    total = sum(sizes)
+    src = [datagen.text(total, datagen.SEED0 + 500), datagen.random_bytes(total, datagen.SEED0 + 501),
+           datagen.structured(total, datagen.SEED0 + 502)]
+    out, at = [], 0
+    for k, size in enumerate(sizes):
+        out.append(src[(0, 0, 1, 2)[k % 4]][at:at + size])
+        at += size
     return out
 
 
@@ -43,9 +49,9 @@ def test_same_bytes_under_every_packing(gpu_ctx, level):
         gpu_ctx.set_table_mode(mode)
         gpu_ctx.set_workspace_limit(limit_gib << 30)
         for rep in range(reps):
-            got = gpu_ctx.compress_blocks(level, blocks[:n])
+            got = gpu_ctx.compress_blocks(level, blocks[:n], comments=["%d bytes" % len(b) for b in blocks[:n]])
             if want is None:
-                want = [ob.compress_block(level, b, "", "") for b in blocks]
+                want = oracle_blocks_mt(level, blocks)   # every block, all host threads (table set-up dominates)
             assert got == want[:n], (level, n, mode, limit_gib, rep)
             plain, segs, status = gpu_ctx.decompress_archive(b"".join(got))
             assert status == 0 and plain == b"".join(blocks[:n]) and all(s["sha1_ok"] == 1 for s in segs), (level, n, mode)

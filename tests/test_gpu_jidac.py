@@ -126,7 +126,8 @@ def test_mirror_class(gpu_ctx):
 def test_large_single_file_and_many_small(gpu_ctx):
     """One file far above the maximum fragment size, and more files than one CTA handles."""
     big = datagen.text(3 << 20, 9)
-    files = [big] + [datagen.text(100 + 37 * i, 1000 + i) for i in range(300)] + [big]
+    pool = datagen.text(4 << 20, 1000)   # one call: every datagen.text call builds an 8 MiB chunk
+    files = [big] + [pool[13001 * i:13001 * i + 100 + 37 * i] for i in range(300)] + [big]
     got, stored = gpu_ctx.jidac_fragment(files, 6, True)
     want, want_stored = ob.jidac_fragment(files, 6, True)
     assert got == want and stored == want_stored
