@@ -9,6 +9,7 @@
 #include <vector>
 
 #include "ctx.h"
+#include "hostlogic.h"
 
 using namespace zg;
 
@@ -170,12 +171,7 @@ int plan_tables(zpaqgpu_ctx *ctx, const Model &m, int n_blocks, size_t other_byt
         ctx->err = "model tables (" + std::to_string(m.ws_bytes) + " bytes per block) exceed the workspace budget";
         return ZPAQGPU_E_NOMEM;
     }
-    u64 slots = std::min<u64>(dense_slots, u64(n_blocks));
-    if (round_cap > 0 && u64(n_blocks) > slots) {
-        const u64 per_round = std::min<u64>(slots, u64(round_cap));
-        const u64 rounds = (u64(n_blocks) + per_round - 1) / per_round;
-        slots = (u64(n_blocks) + rounds - 1) / rounds;
-    }
+    const u64 slots = wave_slots(u64(n_blocks), dense_slots, u64(std::max(0, round_cap)));
     tp.paged = false, tp.slots = int(slots), tp.stride = m.ws_bytes, tp.pool_bytes = 0;
     return ZPAQGPU_OK;
 }
@@ -218,13 +214,7 @@ bool use_chain(const zpaqgpu_ctx *ctx, const Model &m) {
 // as many as spread the launch over all SMs; when that is more than a CTA holds, the CTAs run in rounds, and
 // the rounds are made equal instead of a full one followed by a nearly empty one (-m5 encoder: 1 024 blocks,
 // 6 per CTA at most = 171 CTAs on 148 SMs; 4 per CTA = two rounds of 128).
-int per_cta(const zpaqgpu_ctx *ctx, int n, int most) {
-    const int sms = std::max(1, ctx->sm_count);
-    const int per_sm = (n + sms - 1) / sms;
-    if (per_sm <= most) return std::max(1, per_sm);
-    const int rounds = (n + sms * most - 1) / (sms * most);
-    return std::max(1, std::min(most, (n + rounds * sms - 1) / (rounds * sms)));
-}
+int per_cta(const zpaqgpu_ctx *ctx, int n, int most) { return blocks_per_cta(n, most, ctx->sm_count); }
 
 int pick_warps_per_cta(const zpaqgpu_ctx *ctx, const Model &m, int n_resident) {
     return per_cta(ctx, n_resident, chain_max_warps_per_cta(m));

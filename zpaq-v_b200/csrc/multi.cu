@@ -11,6 +11,7 @@
 #include <vector>
 
 #include "ctx.h"
+#include "hostlogic.h"
 
 using namespace zg;
 
@@ -41,22 +42,6 @@ double now_ms() {
     return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
 }
 
-// world+1 boundaries of contiguous unit ranges balanced by bytes: range g ends at the first unit whose
-// running total reaches total * (g+1) / world.
-std::vector<int> split_by_bytes(const u64 *off, int n, int world) {
-    std::vector<int> b(size_t(world) + 1, n);
-    b[0] = 0;
-    const u64 base = off[0], total = off[n] - base;
-    int k = 1;
-    for (int i = 0; i < n && k < world; ++i) {
-        const u64 acc = off[i + 1] - base;
-        while (k < world && (total == 0 ? i + 1 >= (n * k + world - 1) / world
-                                        : double(acc) >= double(total) * k / world))
-            b[size_t(k++)] = i + 1;
-    }
-    return b;
-}
-
 int first_error(zpaqgpu_multi *m, const std::vector<int> &rcs) {
     for (size_t g = 0; g < rcs.size(); ++g)
         if (rcs[g] != ZPAQGPU_OK) {
@@ -64,22 +49,6 @@ int first_error(zpaqgpu_multi *m, const std::vector<int> &rcs) {
             return rcs[g];
         }
     return ZPAQGPU_OK;
-}
-
-// offset of the first 13-byte locator + "zPQ" at or after `from` (decompressor.v:227-254 looks for these
-// 16 bytes), or len
-u64 next_locator(const uint8_t *arc, u64 len, u64 from) {
-    static const uint8_t tag[16] = {0x37, 0x6b, 0x53, 0x74, 0xa0, 0x31, 0x83, 0xd3,
-                                    0x8c, 0xb2, 0x28, 0xb0, 0xd3, 'z', 'P', 'Q'};
-    u64 p = from;
-    while (p + 16 <= len) {
-        const void *hit = std::memchr(arc + p, tag[0], size_t(len - 15 - p));
-        if (!hit) return len;
-        p = u64(static_cast<const uint8_t *>(hit) - arc);
-        if (std::memcmp(arc + p, tag, 16) == 0) return p;
-        ++p;
-    }
-    return len;
 }
 
 }  // namespace
