@@ -21,7 +21,7 @@ def test_cpp_mirror_roundtrip(tmp_path):
     for level, data in ((1, b"AAAABBBB"), (2, datagen.text(30000)), (0, datagen.random_bytes(70000))):
         r = subprocess.run([exe, str(level)], input=data, capture_output=True, timeout=300)
         assert r.returncode == 0, r.stderr.decode()
-        hexarc, tail, hexjidac = r.stdout.decode().strip().split("\n")
-        assert tail == "1 1 1"
+        hexarc, tail, hexjidac, batch = r.stdout.decode().strip().split("\n")
+        assert tail == "1 1 1" and batch == "batch 1"   # batch: two queued blocks delivered by flush() in order
         assert bytes.fromhex(hexarc) == ob.compress_block(level, data, "test", "")
         assert bytes.fromhex(hexjidac) == ob.jidac_add(["a", "b"], [data, data[::-1]], 20260101120000)

@@ -41,5 +41,24 @@ int main(int argc, char **argv) {
     ja.create_archive({{"a", input}, {"b", std::vector<uint8_t>(input.rbegin(), input.rend())}}, 0);
     for (uint8_t b : jw.bytes()) std::printf("%02x", b);
     std::printf("\n");
-    return same && segs == 1 && ok == 1 ? 0 : 1;
+    // batch mode: two blocks queued, one launch at flush(); the Writer must hold the single block twice
+    zpaq::FileWriter bw;
+    zpaq::Compressor batch(true);
+    batch.set_output(&bw);
+    for (int k = 0; k < 2; ++k) {
+        zpaq::FileReader again(input);
+        batch.set_input(&again);
+        batch.start_block(level);
+        batch.start_segment("test", "");
+        while (batch.compress(65536)) {}
+        batch.end_segment();
+        batch.end_block();
+    }
+    const bool nothing_yet = bw.bytes().empty();
+    batch.flush();
+    std::vector<uint8_t> twice = out.bytes();
+    twice.insert(twice.end(), out.bytes().begin(), out.bytes().end());
+    const bool batch_ok = nothing_yet && bw.bytes() == twice;
+    std::printf("batch %d\n", batch_ok ? 1 : 0);
+    return same && segs == 1 && ok == 1 && batch_ok ? 0 : 1;
 }

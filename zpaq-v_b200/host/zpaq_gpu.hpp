@@ -50,8 +50,12 @@ class Gpu {                           // one context per GPU; no CPU fallback
     zpaqgpu_ctx *c_ = nullptr;
 };
 
+// batch = true is for callers that write many blocks one after the other (cmd/main.v:288-317, one block per
+// file): end_block() queues the block, the queue is coded in ONE launch when it is full or at flush() -- the one
+// call such a caller adds before it closes its output.  Same bytes, same order on the Writer.
 class Compressor {
   public:
+    explicit Compressor(bool batch = false) : batch_(batch) {}
     void set_input(Reader *r) { in_ = r; }
     void set_output(Writer *w) { out_ = w; }
     void start_block(int level) {                                 // compressor.v:79
@@ -81,6 +85,12 @@ class Compressor {
     }
     void end_block() {                                            // compressor.v:402
         if (state_ != Block) return;
+        if (batch_) {
+            const int full = zpaqgpu_block_end_queue(Gpu::ctx());
+            state_ = Start;
+            if (full == 1) flush();
+            return;
+        }
         uint64_t need = 0;
         zpaqgpu_block_end(Gpu::ctx(), nullptr, 0, &need);
         std::vector<uint8_t> blk(need);
@@ -88,10 +98,20 @@ class Compressor {
         if (n > 0 && out_) out_->write(blk.data(), size_t(n));
         state_ = Start;
     }
+    void flush() {                                                // not in the reference: delivers the queue
+        if (state_ != Start) return;
+        uint64_t need = 0;
+        zpaqgpu_flush(Gpu::ctx(), nullptr, 0, &need);             // codes the queue; the bytes are kept
+        if (!need) return;
+        std::vector<uint8_t> all(need);
+        const int64_t n = zpaqgpu_flush(Gpu::ctx(), all.data(), need, &need);
+        if (n > 0 && out_) out_->write(all.data(), size_t(n));
+    }
   private:
     enum { Block, Segment, Start } state_ = Start;                // compressor.v:6-8
     Reader *in_ = nullptr;
     Writer *out_ = nullptr;
+    bool batch_ = false;
 };
 
 class Decompresser {
