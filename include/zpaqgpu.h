@@ -294,6 +294,15 @@ int zpaqgpu_multi_compress_blocks(zpaqgpu_multi *m, int level, const uint8_t *in
 int zpaqgpu_multi_decompress_archive(zpaqgpu_multi *m, const uint8_t *arc, uint64_t len, uint8_t *out,
                                      uint64_t out_cap, uint64_t *out_need, zpaqgpu_segment *segs,
                                      int segs_cap, int *n_segs);
+/* zpaqgpu_jidac_add over all devices -- the one path with an exchange step: every device cuts and hashes a
+ * contiguous range of the files, the (SHA-1, length) lists are merged on the host into one fragment table
+ * (ids count first occurrences in file order, so a duplicate of a file held by another device is stored once),
+ * every device codes the d blocks of the fragments it stores, the first device writes c, h and i blocks.  A d
+ * block never spans devices: the block cut depends on the number of devices, the contents of the archive do
+ * not; with one device the bytes equal zpaqgpu_jidac_add's. */
+int zpaqgpu_multi_jidac_add(zpaqgpu_multi *m, const zpaqgpu_jidac_opts *opts, const char *const *names,
+                            const uint8_t *in, const uint64_t *in_off, int n_files, uint8_t *out,
+                            uint64_t out_cap, uint64_t *out_len, uint64_t *out_need);
 typedef struct {
     int32_t device;          /* CUDA device index                                                */
     int32_t first_unit;      /* first block of the device's range in the last call                */

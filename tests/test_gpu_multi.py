@@ -142,3 +142,50 @@ def test_multi_decompress_falls_back_when_a_block_spans_the_cut(gpu_ctx):
         assert got == gpu_ctx.decompress_archive(bytes(bad)) and got[0] == datagen.text(4000, 70)
     finally:
         m.close()
+
+
+def test_multi_jidac_add(gpu_ctx):
+    """zpaqgpu_multi_jidac_add: one device writes the bytes of zpaqgpu_jidac_add; two devices store a file that
+    both ranges hold once, write exactly what the Python host logic (sharding.jidac_add_sharded, two ranks) writes,
+    and the archive restores every file."""
+    import zpaq_v_b200 as z
+    from zpaq_v_b200 import sharding
+    a, b = datagen.text(60000, 21), datagen.random_bytes(25000, 22)
+    files = {"a.txt": a, "b.bin": b, "c.txt": datagen.text(40000, 23), "empty": b"",
+             "a-copy.txt": a, "d.txt": datagen.text(30000, 24), "b-copy.bin": b, "tail": a[:20000] + b[:5000]}
+    names, fl = list(files), list(files.values())
+    kw = dict(level=1, fragment=2, dedup=True, block_bytes=16384)
+    single = gpu_ctx.jidac_add(names, fl, DATE, **kw)
+    assert single == ob.jidac_add(names, fl, DATE, **kw)
+    one = z.Multi(_devices(1))
+    try:
+        assert one.jidac_add(names, fl, DATE, **kw) == single
+        assert one.jidac_add([], [], DATE, **kw) == gpu_ctx.jidac_add([], [], DATE, **kw)
+    finally:
+        one.close()
+    two = z.Multi(_devices(2))
+    try:
+        arc = two.jidac_add(names, fl, DATE, **kw)
+    finally:
+        two.close()
+    recs = gpu_ctx.jidac_extract(arc)
+    assert {r["name"]: r["data"] for r in recs} == files and all(r["sha1_ok"] == 1 for r in recs)
+    # the same archive from the Python host logic with two ranks played one after the other
+    def frag(fs):
+        return gpu_ctx.jidac_fragment(fs, 2, False)[0]
+
+    def comp(level, blocks, nm, cm):
+        return gpu_ctx.compress_blocks(level, blocks, names=nm, comments=cm)
+
+    box = {}
+    for _ in range(2):
+        arcs = [sharding.jidac_add_sharded(_Rank(2, r, box), frag, comp, names, fl, DATE, level=1, fragment=2,
+                                           block_bytes=16384) for r in (1, 0)]
+    assert arc == arcs[1]
+    # no dedup, one fragment per file, store: the reference's own create_archive bytes through two devices
+    two = z.Multi(_devices(2))
+    try:
+        ref_kw = dict(level=0, fragment=-1, dedup=False, block_bytes=0)
+        assert two.jidac_add(names, fl, DATE, **ref_kw) == ob.jidac_add(names, fl, DATE, **ref_kw)
+    finally:
+        two.close()

@@ -25,7 +25,7 @@ EXPORTS = [
     "zpaqgpu_stream_batch", "zpaqgpu_block_end_queue", "zpaqgpu_queued", "zpaqgpu_flush",
     "zpaqgpu_multi_init", "zpaqgpu_multi_destroy", "zpaqgpu_multi_device_count", "zpaqgpu_multi_ctx",
     "zpaqgpu_multi_last_error", "zpaqgpu_multi_compress_blocks", "zpaqgpu_multi_decompress_archive",
-    "zpaqgpu_multi_last_stats",
+    "zpaqgpu_multi_last_stats", "zpaqgpu_multi_jidac_add",
 ]
 
 
@@ -152,6 +152,7 @@ def lib():
     L.zpaqgpu_multi_compress_blocks.argtypes = [vp, C.c_int, vp, vp, C.c_int, vp, vp, vp, C.c_uint64, vp, u64p]
     L.zpaqgpu_multi_decompress_archive.argtypes = [vp, vp, C.c_uint64, vp, C.c_uint64, u64p, vp, C.c_int, i32p]
     L.zpaqgpu_multi_last_stats.argtypes = [vp, C.c_int, C.POINTER(MultiStats)]
+    L.zpaqgpu_multi_jidac_add.argtypes = [vp, C.POINTER(JidacOpts), vp, vp, vp, C.c_int, vp, C.c_uint64, u64p, u64p]
     _lib = L
     return L
 
@@ -522,6 +523,26 @@ class Multi:
             self._check(rc)
             raw = out.raw
             return [raw[out_off[i]:out_off[i + 1]] for i in range(n)]
+        raise ZpaqGpuError(E_NOSPACE, "output sizing did not converge")
+
+    def jidac_add(self, names, files, date, level=0, fragment=-1, dedup=False, block_bytes=0):
+        """`jidac add` over all devices of the handle (zpaqgpu_multi_jidac_add)."""
+        n, src, off, total = Context._file_ranges(files)
+        arr = (C.c_char_p * max(n, 1))()
+        for i, x in enumerate(names):
+            arr[i] = x.encode() if isinstance(x, str) else x
+        opts = JidacOpts(date, level, fragment, int(dedup), 0, block_bytes)
+        cap = total + total // 4 + 4096 * (n + 4)
+        ln, need = C.c_uint64(0), C.c_uint64(0)
+        for _ in range(2):
+            out = C.create_string_buffer(cap)
+            rc = lib().zpaqgpu_multi_jidac_add(self._h, C.byref(opts), arr, src, off, n, out, cap, C.byref(ln),
+                                               C.byref(need))
+            if rc == E_NOSPACE:
+                cap = need.value + 16
+                continue
+            self._check(rc)
+            return out.raw[:ln.value]
         raise ZpaqGpuError(E_NOSPACE, "output sizing did not converge")
 
     def decompress_archive(self, arc):

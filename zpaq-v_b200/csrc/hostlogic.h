@@ -5,6 +5,7 @@
 #include <algorithm>
 #include <cstdint>
 #include <cstring>
+#include <string>
 #include <vector>
 
 namespace zg {
@@ -64,6 +65,21 @@ inline int blocks_per_cta(int n, int most, int sms) {
     if (per_sm <= most) return std::max(1, per_sm);
     const int rounds = (n + sms * most - 1) / (sms * most);
     return std::max(1, std::min(most, (n + rounds * sms - 1) / (rounds * sms)));
+}
+
+// itos_pad / make_jidac_filename (jidac.v:38-49), the block comment "<usize> jDC\x01" (jidac.v:69, :96) and
+// little-endian fields of the index blocks
+inline std::string pad_num(long long n, int width) {
+    std::string s = std::to_string(n);
+    while (int(s.size()) < width) s = "0" + s;
+    return s;
+}
+inline std::string jidac_name(long long date, char type, uint32_t num) {
+    return "jDC" + pad_num(date, 14) + std::string(1, type) + pad_num(num, 10);
+}
+inline std::string jidac_comment(uint64_t usize) { return std::to_string(usize) + " jDC\x01"; }
+inline void put_le(std::vector<uint8_t> &v, uint64_t x, int bytes) {
+    for (int i = 0; i < bytes; ++i) v.push_back(uint8_t(x >> (8 * i)));
 }
 
 }  // namespace zg

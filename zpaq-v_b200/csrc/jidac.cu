@@ -20,6 +20,7 @@
 #include <vector>
 
 #include "ctx.h"
+#include "hostlogic.h"
 
 using namespace zg;
 
@@ -453,20 +454,6 @@ int jidac_front(zpaqgpu_ctx *ctx, const uint8_t *in, const uint64_t *in_off, int
         R.d_plain = static_cast<const u8 *>(ctx->jd_packed.p);
     }
     return ZPAQGPU_OK;
-}
-
-// itos_pad / make_jidac_filename (jidac.v:38-49)
-std::string pad_num(long long n, int width) {
-    std::string s = std::to_string(n);
-    while (int(s.size()) < width) s = "0" + s;
-    return s;
-}
-std::string jidac_name(long long date, char type, u32 num) {
-    return "jDC" + pad_num(date, 14) + std::string(1, type) + pad_num(num, 10);
-}
-std::string jidac_comment(u64 usize) { return std::to_string(usize) + " jDC\x01"; }  // jidac.v:69, :96
-void put_le(std::vector<u8> &v, u64 x, int bytes) {
-    for (int i = 0; i < bytes; ++i) v.push_back(u8(x >> (8 * i)));
 }
 
 struct DBlock {

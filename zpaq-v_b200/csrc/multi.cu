@@ -8,6 +8,7 @@
 #include <cstring>
 #include <string>
 #include <thread>
+#include <unordered_map>
 #include <vector>
 
 #include "ctx.h"
@@ -24,6 +25,8 @@ struct zpaqgpu_multi {
     std::vector<zpaqgpu_stats> stats;
     std::vector<float> stage_ms, fetch_ms;
     int fallback_single = 0;  // last decompress call was repeated on one device (see below)
+    zpaqgpu_ctx *aux = nullptr;  // second context on the first device: index blocks of jidac add, coded while
+                                 // that device still holds its d blocks
 };
 
 namespace {
@@ -93,6 +96,7 @@ int zpaqgpu_multi_init(zpaqgpu_multi **out, const int *devices, int n_devices) {
 
 void zpaqgpu_multi_destroy(zpaqgpu_multi *m) {
     if (!m) return;
+    if (m->aux) zpaqgpu_destroy(m->aux);
     for (zpaqgpu_ctx *c : m->ctx) zpaqgpu_destroy(c);
     delete m;
 }
@@ -274,6 +278,244 @@ int zpaqgpu_multi_decompress_archive(zpaqgpu_multi *m, const uint8_t *arc, uint6
     });
     if ((rc = first_error(m, rcs))) return rc;
     return part[size_t(last)].status;
+    });
+}
+
+// `jidac add` over all devices of the handle (north_star: "jidac add ... 8 x B200").  The one path with an
+// exchange step: a duplicate of a file that another device holds can only be found through the fragment
+// digests of every device.
+//   1. files are split into contiguous ranges balanced by bytes; every device cuts and hashes its range
+//      (zpaqgpu_jidac_fragment: rolling-hash fragmentation + SHA-1 kernels);
+//   2. EXCHANGE, on the host: the (SHA-1, length) lists are merged in file order into one table -- ids count
+//      first occurrences (jidac.v:153-163), a later equal fragment, on whichever device, takes the id of the
+//      first; 24 bytes per fragment cross the host, no payload does;
+//   3. every device packs the fragments it stores (first occurrences inside its range) into d blocks of up
+//      to block_bytes and codes them; a d block never spans devices, so the block cut depends on the number
+//      of devices, the contents of the archive do not (one device: the bytes of zpaqgpu_jidac_add);
+//   4. c, h and i blocks (jidac.v:216-295) are written by the first device; every device then copies its d
+//      blocks to their place behind the c block.
+int zpaqgpu_multi_jidac_add(zpaqgpu_multi *m, const zpaqgpu_jidac_opts *opts, const char *const *names,
+                            const uint8_t *in, const uint64_t *in_off, int n_files, uint8_t *out, uint64_t out_cap,
+                            uint64_t *out_len, uint64_t *out_need) {
+    return zg::guarded<int>(static_cast<zpaqgpu_ctx *>(nullptr), [&]() -> int {
+    if (!m || !opts || n_files < 0 || (n_files > 0 && (!in_off || !names))) return ZPAQGPU_E_ARG;
+    if (opts->level < 0 || opts->level > 5 || opts->fragment < -1 || opts->fragment > 40) return ZPAQGPU_E_ARG;
+    if (out_len) *out_len = 0;
+    if (out_need) *out_need = 0;
+    const int G = int(m->ctx.size());
+    m->fallback_single = 0;
+    std::vector<int> cut(size_t(G) + 1, 0);
+    if (n_files > 0) cut = split_by_bytes(in_off, n_files, G);
+    std::vector<int> rcs(size_t(G), ZPAQGPU_OK);
+    int rc;
+    // 1. fragments of every range
+    std::vector<std::vector<zpaqgpu_fragment>> frs(static_cast<size_t>(G));
+    on_every_device(G, [&](int g) {
+        const int lo = cut[size_t(g)], n = cut[size_t(g) + 1] - lo;
+        m->first_unit[size_t(g)] = lo, m->n_units[size_t(g)] = n;
+        m->stats[size_t(g)] = zpaqgpu_stats{};
+        m->stage_ms[size_t(g)] = m->fetch_ms[size_t(g)] = 0.f;
+        if (n == 0) return;
+        const double t0 = now_ms();
+        const u64 bytes = in_off[lo + n] - in_off[lo];
+        const u64 smallest = opts->fragment < 0 ? ~0ull : (64ull << std::min(opts->fragment, 40));
+        int cap = int(std::min<u64>(bytes / std::max<u64>(smallest, 1) + u64(n) + 16, 1u << 30));
+        for (int attempt = 0; attempt < 2; ++attempt) {
+            frs[size_t(g)].resize(size_t(cap));
+            int nf = 0, ns = 0;
+            rcs[size_t(g)] = zpaqgpu_jidac_fragment(m->ctx[size_t(g)], in, in_off + lo, n, opts->fragment, 0,
+                                                    frs[size_t(g)].data(), cap, &nf, &ns);
+            if (rcs[size_t(g)] == ZPAQGPU_E_NOSPACE && attempt == 0) {
+                cap = nf + 16;
+                continue;
+            }
+            if (rcs[size_t(g)] == ZPAQGPU_OK) frs[size_t(g)].resize(size_t(nf));
+            break;
+        }
+        m->stage_ms[size_t(g)] = float(now_ms() - t0);
+    });
+    if ((rc = first_error(m, rcs))) return rc;
+    // 2. the exchange: one table over all devices, in file order
+    struct Key {
+        uint8_t b[24];
+        bool operator==(const Key &o) const { return std::memcmp(b, o.b, 24) == 0; }
+    };
+    struct KeyHash {
+        size_t operator()(const Key &k) const {
+            uint64_t v;
+            std::memcpy(&v, k.b, 8);
+            return size_t(v);
+        }
+    };
+    struct GFrag {
+        u32 file, id, len;
+        const uint8_t *sha1;
+    };
+    std::vector<GFrag> all;                       // every fragment, file order
+    std::vector<std::vector<u32>> stored_of(static_cast<size_t>(G));  // per device: indices into `all` it stores
+    std::unordered_map<Key, u32, KeyHash> seen;
+    u32 next_id = 0;
+    for (int g = 0; g < G; ++g)
+        for (const zpaqgpu_fragment &f : frs[size_t(g)]) {
+            GFrag e{f.file + u32(cut[size_t(g)]), 0, u32(f.len), f.sha1};
+            bool first = true;
+            if (opts->dedup) {
+                Key k;
+                std::memcpy(k.b, f.sha1, 20);
+                const u32 l = u32(f.len);
+                std::memcpy(k.b + 20, &l, 4);
+                auto it = seen.find(k);
+                if (it != seen.end()) e.id = it->second, first = false;
+                else seen.emplace(k, next_id + 1);
+            }
+            if (first) {
+                e.id = ++next_id;
+                stored_of[size_t(g)].push_back(u32(all.size()));
+            }
+            all.push_back(e);
+        }
+    // 3. d blocks of every device: stored fragments in id order, packed up to block_bytes (jidac.v:186-214)
+    struct DB {
+        u32 first_id;
+        u64 len;
+        std::vector<u32> frags;  // indices into `all`
+    };
+    std::vector<std::vector<DB>> dbs(static_cast<size_t>(G));
+    std::vector<u64> totals(size_t(G), 0);
+    std::vector<std::vector<u64>> d_sizes(static_cast<size_t>(G));
+    const std::vector<uint8_t> hdr = level_header(opts->level);
+    Model model;
+    if ((rc = model_from_level_layout(hdr.data(), int(hdr.size()), model))) return m->err = model.error, rc;
+    // where each fragment's bytes are: fragment k of device g sits at in + frs[g][k].off (absolute in `in`? no:
+    // zpaqgpu_jidac_fragment reports offsets inside `in`), so keep the source pointer beside the table
+    std::vector<const uint8_t *> src_of(all.size());
+    {
+        size_t at = 0;
+        for (int g = 0; g < G; ++g)
+            for (const zpaqgpu_fragment &f : frs[size_t(g)]) src_of[at++] = in + f.off;
+    }
+    on_every_device(G, [&](int g) {
+        std::vector<DB> &blocks = dbs[size_t(g)];
+        for (u32 k : stored_of[size_t(g)]) {
+            const GFrag &f = all[k];
+            const bool fresh = blocks.empty() || opts->block_bytes == 0 || blocks.back().len + f.len > opts->block_bytes;
+            if (fresh) blocks.push_back(DB{f.id, 0, {}});
+            blocks.back().len += f.len, blocks.back().frags.push_back(k);
+        }
+        const int nd = int(blocks.size());
+        if (nd == 0) return;
+        const double t0 = now_ms();
+        // the plaintext of the d blocks: the stored fragments back to back (duplicates skipped), gathered on
+        // the host from the caller's buffer, then one upload
+        u64 bytes = 0;
+        for (const DB &b : blocks) bytes += b.len;
+        std::vector<uint8_t> plain(static_cast<size_t>(bytes));
+        std::vector<u64> off(size_t(nd) + 1, 0);
+        std::vector<std::string> nm(static_cast<size_t>(nd)), cm(static_cast<size_t>(nd));
+        std::vector<const char *> nmp(static_cast<size_t>(nd)), cmp(static_cast<size_t>(nd));
+        u64 at = 0;
+        for (int b = 0; b < nd; ++b) {
+            off[size_t(b)] = at;
+            for (u32 k : blocks[size_t(b)].frags) {
+                if (all[k].len) std::memcpy(plain.data() + at, src_of[k], all[k].len);
+                at += all[k].len;
+            }
+            nm[size_t(b)] = jidac_name(opts->date, 'd', blocks[size_t(b)].first_id);
+            cm[size_t(b)] = jidac_comment(blocks[size_t(b)].len);
+            nmp[size_t(b)] = nm[size_t(b)].c_str(), cmp[size_t(b)] = cm[size_t(b)].c_str();
+        }
+        off[size_t(nd)] = at;
+        rcs[size_t(g)] = zg::guarded<int>(m->ctx[size_t(g)], [&]() -> int {
+            int r = compress_stage(m->ctx[size_t(g)], model, plain.data(), off.data(), nd, nmp.data(), cmp.data(),
+                                   &totals[size_t(g)]);
+            if (r) return r;
+            // the coded size of every d block goes into its h block
+            d_sizes[size_t(g)].assign(size_t(nd) + 1, 0);
+            zpaqgpu_ctx *c = m->ctx[size_t(g)];
+            if (cudaSetDevice(c->device) != cudaSuccess) return ZPAQGPU_E_CUDA;
+            if (cudaMemcpyAsync(d_sizes[size_t(g)].data(), c->out_off.p, 8 * size_t(nd + 1), cudaMemcpyDeviceToHost,
+                                c->stream) != cudaSuccess ||
+                cudaStreamSynchronize(c->stream) != cudaSuccess)
+                return ZPAQGPU_E_CUDA;
+            return ZPAQGPU_OK;
+        });
+        m->stats[size_t(g)] = m->ctx[size_t(g)]->stats;
+        m->stage_ms[size_t(g)] += float(now_ms() - t0);
+    });
+    if ((rc = first_error(m, rcs))) return rc;
+    u64 total_d = 0;
+    for (u64 t : totals) total_d += t;
+    // 4. c, h and i blocks, all store mode (jidac.v:67-91, :216-295)
+    std::vector<uint8_t> small;
+    std::vector<u64> s_off{0};
+    std::vector<std::string> s_name, s_comment;
+    auto close_block = [&](char type, u32 num) {
+        s_name.push_back(jidac_name(opts->date, type, num));
+        s_comment.push_back(jidac_comment(small.size() - s_off.back()));
+        s_off.push_back(small.size());
+    };
+    put_le(small, total_d, 8);
+    close_block('c', next_id + 1);
+    for (int g = 0; g < G; ++g)
+        for (size_t b = 0; b < dbs[size_t(g)].size(); ++b) {
+            const DB &d = dbs[size_t(g)][b];
+            put_le(small, u32(d_sizes[size_t(g)][b + 1] - d_sizes[size_t(g)][b]), 4);
+            for (u32 k : d.frags) {
+                small.insert(small.end(), all[k].sha1, all[k].sha1 + 20);
+                put_le(small, all[k].len, 4);
+            }
+            close_block('h', d.first_id);
+        }
+    {
+        size_t fi = 0;
+        for (int f = 0; f < n_files; ++f) {
+            put_le(small, u64(opts->date), 8);
+            for (const char *c = names[f] ? names[f] : ""; *c; ++c) small.push_back(uint8_t(*c));
+            small.push_back(0);
+            size_t fe = fi;
+            while (fe < all.size() && all[fe].file == u32(f)) ++fe;
+            if (opts->date != 0) {
+                put_le(small, 0, 4);
+                put_le(small, u32(fe - fi), 4);
+                for (size_t k = fi; k < fe; ++k) put_le(small, all[k].id, 4);
+            }
+            fi = fe;
+        }
+        if (small.size() > s_off.back()) close_block('i', 1);
+    }
+    const int ns = int(s_name.size());
+    std::vector<const char *> snp(static_cast<size_t>(ns)), scp(static_cast<size_t>(ns));
+    for (int b = 0; b < ns; ++b) snp[size_t(b)] = s_name[size_t(b)].c_str(), scp[size_t(b)] = s_comment[size_t(b)].c_str();
+    if (!m->aux && (rc = zpaqgpu_init(&m->aux, m->devices[0]))) return rc;
+    const u64 cap2 = small.size() + small.size() / 4096 + 256 * u64(ns) + 4096;
+    std::vector<uint8_t> idx(static_cast<size_t>(cap2));
+    std::vector<u64> o2(size_t(ns) + 1, 0);
+    u64 need2 = 0;
+    rc = zpaqgpu_compress_blocks(m->aux, 0, small.data(), s_off.data(), ns, snp.data(), scp.data(), idx.data(), cap2,
+                                 o2.data(), &need2);
+    if (rc) return m->err = std::string("index blocks: ") + m->aux->err, rc;
+    const u64 total_s = o2[size_t(ns)], c_len = o2[1], total = total_d + total_s;
+    if (out_len) *out_len = total;
+    if (out_need) *out_need = total;
+    if (total > out_cap) return ZPAQGPU_E_NOSPACE;
+    if (!out) return ZPAQGPU_E_ARG;
+    // archive order: c block, d blocks (device order = id order), h blocks, i block (jidac.v:221-295)
+    std::memcpy(out, idx.data(), size_t(c_len));
+    std::vector<u64> base(size_t(G) + 1, c_len);
+    for (int g = 0; g < G; ++g) base[size_t(g) + 1] = base[size_t(g)] + totals[size_t(g)];
+    on_every_device(G, [&](int g) {
+        const int nd = int(dbs[size_t(g)].size());
+        if (nd == 0) return;
+        const double t0 = now_ms();
+        std::vector<u64> off(size_t(nd) + 1);
+        rcs[size_t(g)] = zg::guarded<int>(m->ctx[size_t(g)], [&]() -> int {
+            return compress_fetch(m->ctx[size_t(g)], nd, totals[size_t(g)], out + base[size_t(g)], off.data(), 0);
+        });
+        m->fetch_ms[size_t(g)] = float(now_ms() - t0);
+    });
+    if ((rc = first_error(m, rcs))) return rc;
+    if (total_s > c_len) std::memcpy(out + c_len + total_d, idx.data() + c_len, size_t(total_s - c_len));
+    return ZPAQGPU_OK;
     });
 }
 
