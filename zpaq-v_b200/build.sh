@@ -13,7 +13,7 @@ for f in $CU; do
   [ -f csrc/$f.cu ] || continue
   stale=0
   [ -f build/$f.o ] || stale=1
-  for dep in csrc/$f.cu csrc/common.cuh csrc/kernels.h csrc/model.h csrc/ctx.h csrc/hostlogic.h ../include/zpaqgpu.h; do
+  for dep in csrc/$f.cu csrc/common.cuh csrc/kernels.h csrc/model.h csrc/ctx.h csrc/hostlogic.h csrc/sha1_lane.h ../include/zpaqgpu.h; do
     [ $stale -eq 0 ] && [ $dep -nt build/$f.o ] && stale=1
   done
   if [ $stale -eq 1 ]; then

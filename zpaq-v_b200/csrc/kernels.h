@@ -69,7 +69,7 @@ int tree2_max_pairs_per_cta(const Model &m);
 struct ShaJob {
     u64 off, len;  // byte range inside `base`
 };
-// k_sha1_segments: one thread per job; digests[j*20..] (sha1.v:42-146)
+// k_sha1_segments: one byte range per lane, staged through shared memory; digests[j*20..] (sha1.v:42-146)
 void launch_sha1(const u8 *base, const ShaJob *jobs, int n_jobs, u8 *digests, cudaStream_t s);
 
 // k_fill_workspace: writes the non-zero initial table images into every workspace slot

@@ -3,6 +3,10 @@
 #include "../../include/zpaqgpu.h"
 #include "common.cuh"
 #include "kernels.h"
+#include "sha1_lane.h"
+
+#include <cstdlib>
+#include <cstring>
 
 namespace zg {
 
@@ -34,7 +38,82 @@ void launch_fill(const FillArgs &A, cudaStream_t s) {
 }
 
 // ------------------------------------------------------------------------------------------
-// k_sha1_segments: SHA-1 of each byte range, one thread per range (sha1.v:42-146).
+// k_sha1_segments: SHA-1 of each byte range (sha1.v:42-146), one range per lane, one warp per CTA.
+//
+// A hash is one serial chain (80 rounds of two dependent operations per 64 bytes), so a range belongs to one
+// lane and the kernel's time is that of its longest range; what the warp shares is the memory side.  The
+// ranges start at any byte (jidac fragments) and lie megabytes apart, so a lane loading its own range would
+// issue 32 separate sector requests per instruction and, unaligned, one per BYTE.  Instead the warp brings
+// 272 bytes (four blocks and the 16 bytes an unaligned block can spill into) of every lane's range into
+// shared memory with 16-byte cp.async copies -- lane t of the warp copies chunk t of a row, so a row is one
+// coalesced request -- two rounds deep, so that the copies of round r + 1 fly while round r is hashed.  The
+// lane then takes its 16 big-endian words from its row with PRMT at whatever alignment the range has, and
+// makes the padding blocks from the same window (sha1_lane.h; the identical code runs under a host emulation
+// of the warp in tests/test_sha1_lane.py).  Nothing outside a range is ever read: the first and last chunk
+// of an unaligned range are copied byte by byte.
+// ------------------------------------------------------------------------------------------
+namespace {
+__device__ __forceinline__ void cp_async16(void *smem_dst, u64 gmem_src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(u32(__cvta_generic_to_shared(smem_dst))), "l"(gmem_src)
+                 : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all_but_one() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
+}  // namespace
+
+__global__ void __launch_bounds__(32) k_sha1_segments(const u8 *base, const ShaJob *jobs, int n_jobs, u8 *digests) {
+    using namespace sha1lane;
+    __shared__ __align__(16) u8 buf[2][32 * kRowBytes];
+    __shared__ u64 desc[32][3];   // per row: window origin, first byte, one past the last
+    const int lane = threadIdx.x;
+    const int j = blockIdx.x * 32 + lane;
+    const bool has = j < n_jobs;
+    Lane L;
+    lane_begin(L, reinterpret_cast<u64>(base) + (has ? jobs[j].off : 0ull), has ? jobs[j].len : 0ull, has);
+    desc[lane][0] = L.a, desc[lane][1] = L.s, desc[lane][2] = L.end;
+    const u32 n_rounds = __reduce_max_sync(0xFFFFFFFFu, lane_rounds(L));
+    __syncwarp();
+    auto issue = [&](u32 r) {
+        u8 *stage = buf[r & 1];
+#pragma unroll 1
+        for (u32 i = 0; i < kChunksPerRow; ++i) {
+            const u32 q = u32(lane) + 32u * i;
+            const u32 row = q / kChunksPerRow, c = q - row * kChunksPerRow;
+            u64 src;
+            u32 lo = 0, hi = 0;
+            const ChunkKind kind = chunk_plan(desc[row][0], desc[row][1], desc[row][2], r, c, src, lo, hi);
+            u8 *dst = stage + row * kRowBytes + 16u * c;
+            if (kind == kWhole) {
+                cp_async16(dst, src);
+            } else if (kind == kPart) {
+                for (u32 t = lo; t < hi; ++t) dst[t] = *reinterpret_cast<const u8 *>(src + t);
+            }
+        }
+    };
+    if (n_rounds) issue(0);
+    cp_async_commit();
+    for (u32 r = 0; r < n_rounds; ++r) {
+        if (r + 1 < n_rounds) issue(r + 1);
+        cp_async_commit();            // (an empty group on the last round keeps the count uniform)
+        cp_async_wait_all_but_one();  // round r has landed; round r + 1 may still be in flight
+        __syncwarp();
+        const u32 *row = reinterpret_cast<const u32 *>(buf[r & 1] + lane * kRowBytes);
+#pragma unroll 1
+        for (u32 k = 0; k < kBlocksPerRound; ++k) {
+            if (r * kBlocksPerRound + k < L.total) {
+                u32 w[16];
+                block_words(L, row, r, k, w);
+                compress(L.st, w);
+            }
+        }
+        __syncwarp();                 // the stage is free for round r + 2
+    }
+    if (has) digest_bytes(L, digests + u64(j) * 20);
+}
+
+// ------------------------------------------------------------------------------------------
+// k_sha1_direct: the kernel k_sha1_segments replaced -- every lane loads its own range (16-byte loads when
+// the range is aligned, bytes otherwise).  Kept as the A/B arm (ZPAQGPU_SHA1=direct).
 // ------------------------------------------------------------------------------------------
 namespace {
 __device__ __forceinline__ u32 rol(u32 x, int n) { return __funnelshift_l(x, x, n); }
@@ -65,7 +144,7 @@ __device__ void sha1_compress(u32 st[5], const u32 blockw[16]) {
 }
 }  // namespace
 
-__global__ void k_sha1_segments(const u8 *base, const ShaJob *jobs, int n_jobs, u8 *digests) {
+__global__ void k_sha1_direct(const u8 *base, const ShaJob *jobs, int n_jobs, u8 *digests) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= n_jobs) return;
     const u8 *p = base + jobs[j].off;
@@ -114,10 +193,16 @@ __global__ void k_sha1_segments(const u8 *base, const ShaJob *jobs, int n_jobs, 
     }
 }
 
+
 void launch_sha1(const u8 *base, const ShaJob *jobs, int n_jobs, u8 *digests, cudaStream_t s) {
     if (n_jobs <= 0) return;
-    // 32 threads per CTA spreads the serial hashes over as many SMs as possible
-    k_sha1_segments<<<(n_jobs + 31) / 32, 32, 0, s>>>(base, jobs, n_jobs, digests);
+    // one warp per CTA spreads the serial hashes over as many SMs as possible
+    static const bool direct = [] {
+        const char *v = std::getenv("ZPAQGPU_SHA1");
+        return v && std::strcmp(v, "direct") == 0;
+    }();
+    if (direct) k_sha1_direct<<<(n_jobs + 31) / 32, 32, 0, s>>>(base, jobs, n_jobs, digests);
+    else k_sha1_segments<<<(n_jobs + 31) / 32, 32, 0, s>>>(base, jobs, n_jobs, digests);
 }
 
 // ------------------------------------------------------------------------------------------
