@@ -55,7 +55,7 @@ struct zpaqgpu_ctx {
     bool ahead = true;         // ZPAQGPU_AHEAD=0: the encoder on paged tables reads page-table entries when it probes (A/B against the PAGED variant)
     bool spec_probe = true;    // ZPAQGPU_SPEC_PROBE=0: the chain decoders probe only once a nibble is complete
     int decoder = 1;           // ZPAQGPU_DECODER in the environment: serial (0, one bit at a time), tree (1, one warp per
-                               // block), tree2 (2, two warps per block; the default where the model allows it)
+                               // block; the default), tree2 (2, two warps per block where the model allows it; opt-in)
     zg::u64 ws_limit = 0;
     int sm_count = 148;
     std::string err;
