@@ -6,6 +6,7 @@
 // then every device copies its bytes to its final place in the caller's buffer.
 #include <algorithm>
 #include <cstring>
+#include <exception>
 #include <string>
 #include <thread>
 #include <unordered_map>
@@ -31,12 +32,30 @@ struct zpaqgpu_multi {
 
 namespace {
 
+// f(g) on one host thread per device (device 0 on the caller's).  An exception in any of them (an allocation
+// of host memory that fails) is held until every thread has been joined and then rethrown on the caller's
+// thread, where the guarded entry point turns it into a status: no exception leaves a std::thread and no
+// joinable thread is ever destroyed.
 template <class F>
 void on_every_device(int n, F &&f) {
+    std::vector<std::exception_ptr> thrown(static_cast<size_t>(std::max(n, 1)));
+    auto run = [&f, &thrown](int g) {
+        try {
+            f(g);
+        } catch (...) {
+            thrown[size_t(g)] = std::current_exception();
+        }
+    };
     std::vector<std::thread> th;
-    for (int g = 1; g < n; ++g) th.emplace_back([&f, g] { f(g); });
-    f(0);
+    try {
+        for (int g = 1; g < n; ++g) th.emplace_back(run, g);
+    } catch (...) {   // a thread could not be started: the devices without one are reported, the others joined
+        thrown[0] = std::current_exception();
+    }
+    if (!thrown[0]) run(0);
     for (auto &t : th) t.join();
+    for (const std::exception_ptr &e : thrown)
+        if (e) std::rethrow_exception(e);
 }
 
 double now_ms() {
