@@ -210,7 +210,9 @@ def config_dict(args):
     return {"workload": "-m%d, %d x %d KiB independent blocks of synthetic text per GPU (BASELINE.json configs[1])"
                         % (args.level, args.blocks, args.block_kib),
             "level": args.level, "blocks_per_gpu": args.blocks, "block_bytes": args.block_kib * 1024,
-            "l2": "inputs (%d MiB per GPU) exceed the 126 MB L2, no flush needed" % (args.blocks * args.block_kib // 1024),
+            "l2": ("inputs (%d MiB per GPU) exceed the 126 MB L2, no flush needed" if args.blocks * args.block_kib * 1024 > 126e6
+                   else "inputs (%d MiB per GPU) FIT the 126 MB L2 and nothing flushes it between steps: a smoke "
+                        "configuration, not a bench line") % (args.blocks * args.block_kib // 1024),
             "parallelism": "one ZPAQ block per warp group; disjoint block ranges per GPU, no collective"}
 
 
