@@ -10,4 +10,4 @@ PY
 python tools/exp_paged.py > gpurun_out/r02_exp_paged.jsonl 2>&1; cat gpurun_out/r02_exp_paged.jsonl
 ncu --set full --clock-control none --import-source on -k 'regex:k_decode_genwarp' -c 1 -o gpurun_out/r02_genwarp_dec python bench.py --steps 1 --warmup 1 --no-e2e --no-cpu-baseline --blocks 64 --block-kib 64 --per-level generic > gpurun_out/r02_ncu_genwarp.log 2>&1
 ls -la gpurun_out/r02_genwarp_dec.ncu-rep
-sh tools/r02_sanitize.sh
+sh tools/runs/r02_sanitize.sh
