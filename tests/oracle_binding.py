@@ -20,10 +20,12 @@ def lib():
     global _LIB
     if _LIB is not None:
         return _LIB
-    path = os.path.join(ORACLE_DIR, "libzpaq_oracle.so")
-    src = os.path.join(ORACLE_DIR, "zpaq_oracle.c")
-    if not os.path.exists(path) or (os.path.exists(src) and os.path.getmtime(src) > os.path.getmtime(path)):
-        build()
+    path = os.environ.get("ZPAQ_ORACLE_SO")   # another build of the same sources (tests/test_oracle_ubsan.py)
+    if not path:
+        path = os.path.join(ORACLE_DIR, "libzpaq_oracle.so")
+        src = os.path.join(ORACLE_DIR, "zpaq_oracle.c")
+        if not os.path.exists(path) or (os.path.exists(src) and os.path.getmtime(src) > os.path.getmtime(path)):
+            build()
     L = C.CDLL(path)
     u8p, u64p = C.POINTER(C.c_uint8), C.POINTER(C.c_uint64)
     L.zo_squash_table.restype = C.POINTER(C.c_int32)
