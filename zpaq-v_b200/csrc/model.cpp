@@ -305,8 +305,8 @@ int build_layout(Model &m, bool paged) {
         }
         case C_MIX: {
             c.a = P(1);
-            const int size = 1 << c.a, j = P(2), mm = P(3);
             if (c.a > 22) return m.error = "MIX sizebits > 22", ZPAQGPU_E_UNSUPPORTED;
+            const int size = 1 << c.a, j = P(2), mm = P(3);
             if (mm == 0) return m.error = "MIX with m=0 (the reference divides by zero)", ZPAQGPU_E_FORMAT;
             c.b = j, c.c = size, c.limit = mm;
             c.p[0] = uint32_t(P(4)), c.p[1] = uint32_t(P(5));
